@@ -1,0 +1,93 @@
+"""ctypes binding of libevo_b200.so (the C ABI declared in include/evo_b200.h).
+
+There is no CPU fallback and no other backend: if the shared library is missing or a
+call fails, this module raises.  Build it with ``python -m evo_b200.build``."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libevo_b200.so")
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_RESID, EPI_RESID, EPI_GELU_GATE = range(5)
+
+
+class EvoError(RuntimeError):
+    pass
+
+
+class GemmParams(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int64),
+                ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("epilogue", C.c_int), ("variant", C.c_int)]
+
+
+class HyenaParams(C.Structure):
+    _fields_ = [("z", C.c_void_p), ("y", C.c_void_p), ("fir_w", C.c_void_p), ("fir_b", C.c_void_p), ("Dskip", C.c_void_p),
+                ("poles", C.c_void_p), ("residues", C.c_void_p),
+                ("B", C.c_int), ("L", C.c_int64), ("D", C.c_int), ("S", C.c_int), ("nheads", C.c_int),
+                ("halo", C.c_void_p), ("state_in", C.c_void_p), ("state_out", C.c_void_p), ("fir_state_out", C.c_void_p),
+                ("force_segments", C.c_int), ("state_only", C.c_int)]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+                ("q_tok_stride", C.c_int64), ("kv_tok_stride", C.c_int64),
+                ("q_batch_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
+                ("B", C.c_int), ("Lq", C.c_int64), ("Lk", C.c_int64), ("H", C.c_int), ("hd", C.c_int),
+                ("q_pos0", C.c_int64), ("softmax_scale", C.c_float)]
+
+
+# name -> (restype, argtypes); every symbol include/evo_b200.h declares
+SIGNATURES = {
+    "evo_last_error": (C.c_char_p, []),
+    "evo_abi_version": (C.c_int, []),
+    "evo_launch_count": (C.c_int64, []),
+    "evo_reset_launch_count": (None, []),
+    "evo_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "evo_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "evo_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "evo_gemm_cublaslt_reference": (C.c_int, [C.POINTER(GemmParams), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "evo_hyena_fwd_workspace": (C.c_size_t, [C.POINTER(HyenaParams)]),
+    "evo_hyena_fwd": (C.c_int, [C.POINTER(HyenaParams), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "evo_hyena_step": (C.c_int, [C.c_void_p] * 9 + [C.c_int] * 4 + [C.c_void_p]),
+    "evo_hyena_combine_states": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "evo_rope_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "evo_rotary_qk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "evo_attn_fwd_workspace": (C.c_size_t, [C.POINTER(AttnParams), C.c_int]),
+    "evo_attn_fwd_ws": (C.c_int, [C.POINTER(AttnParams), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "evo_attn_fwd_simple": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
+    "evo_kv_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
+    "evo_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "evo_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library (loads on first use; raises if it is not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EvoError(f"{LIB_PATH} is missing: the CUDA extension is not built (run `python -m evo_b200.build`). "
+                           "evo_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().evo_last_error()
+        raise EvoError(f"{what or 'evo_b200'} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

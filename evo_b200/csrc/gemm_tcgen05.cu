@@ -1,0 +1,301 @@
+// Tensor-core linear layers for sm_100a: C[M,N] = epilogue(A[M,K] . W[N,K]^T).
+//
+// Persistent, warp-specialised tcgen05 kernel:
+//   warp 0   TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1   MMA issuer     (one thread issues tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue      (tcgen05.ld -> fused bias / residual / GELU-gate -> bf16 -> HBM)
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
+// overlaps the mainloop of tile i+1.
+//
+// CG = 1: one CTA per 128 x 256 output tile (UMMA 128x256x16), 4-stage ring.
+// CG = 2: a CTA pair (cluster 2x1) per 256 x 256 tile (UMMA 256x256x16, cta_group::2): each
+//         CTA stages its own 128 rows of A and 128 rows of W, halving per-SM operand traffic;
+//         6-stage ring.  The leader CTA issues the MMAs and multicasts the completions.
+//
+// Epilogues reproduce the reference's bf16 rounding points (nn.Linear output is rounded to
+// bf16 before the residual add / the gate): see include/evo_b200.h.
+#include "common.cuh"
+#include "../../include/evo_b200.h"
+
+using namespace evo;
+
+namespace {
+
+constexpr int BM = 128;            // rows of C per CTA
+constexpr int BN = 256;            // columns of C per tile (UMMA N)
+constexpr int BK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UK = 16;             // UMMA K for 16-bit inputs
+constexpr int NTHREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+template <int CG> struct Cfg {
+  static constexpr int B_ROWS = BN / CG;                       // W rows staged per CTA
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = CG == 1 ? 4 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+  bf16* C; long long ldc;
+  const bf16* bias;
+  const bf16* resid; long long ldr;
+  long long M, N, K;
+  int m_blocks, n_blocks, group_m;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// grouped rasterisation: GROUP_M row-blocks share the sweep over n so their A tiles stay in L2
+__device__ __forceinline__ void tile_coords(int tile, const GemmArgs& g, int& m_blk, int& n_blk) {
+  int per_group = g.group_m * g.n_blocks;
+  int grp = tile / per_group;
+  int first_m = grp * g.group_m;
+  int gm = min(g.group_m, g.m_blocks - first_m);
+  int in = tile - grp * per_group;
+  m_blk = first_m + in % gm;
+  n_blk = in / gm;
+}
+
+template <int EPI>
+__device__ __forceinline__ void store_chunk(const GemmArgs& g, long long row, int col, const uint32_t (&acc)[32], const uint32_t (&acc2)[32]) {
+  // acc: 32 consecutive fp32 accumulator columns of this thread's row (as raw bits)
+  uint32_t outw[16];
+  if constexpr (EPI == EVO_EPI_GELU_GATE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a0 = rbf(__uint_as_float(acc[2 * j])), a1 = rbf(__uint_as_float(acc[2 * j + 1]));
+      float b0 = rbf(__uint_as_float(acc2[2 * j])), b1 = rbf(__uint_as_float(acc2[2 * j + 1]));
+      outw[j] = pack_bf16(rbf(gelu_erf(a0)) * b0, rbf(gelu_erf(a1)) * b1);
+    }
+  } else {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    if constexpr (EPI == EVO_EPI_BIAS || EPI == EVO_EPI_BIAS_RESID) {
+      const uint4* bp = reinterpret_cast<const uint4*>(g.bias + col);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 bv = __ldg(bp + q);
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[q * 8 + 2 * j] += bf_lo(bw[j]); v[q * 8 + 2 * j + 1] += bf_hi(bw[j]); }
+      }
+    }
+    if constexpr (EPI == EVO_EPI_BIAS_RESID || EPI == EVO_EPI_RESID) {
+      const uint4* rp = reinterpret_cast<const uint4*>(g.resid + row * g.ldr + col);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 rv = __ldg(rp + q);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[q * 8 + 2 * j] = rbf(v[q * 8 + 2 * j]) + bf_lo(rw[j]);
+          v[q * 8 + 2 * j + 1] = rbf(v[q * 8 + 2 * j + 1]) + bf_hi(rw[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) outw[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(g.C + row * g.ldc + col);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dst[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
+}
+
+template <int CG, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  using C_ = Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + C_::STAGES * C_::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint64_t* empty = full + C_::STAGES;
+  uint64_t* tfull = empty + C_::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C_::STAGES; ++i) { mbar_init(&full[i], CG); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc<CG>(tmem_slot, 512); tmem_relinquish<CG>(); }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = g.m_blocks * g.n_blocks;           // m_blocks counts (BM*CG)-row blocks
+  const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int nkb = (int)(g.K / BK);
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t full_leader_mask = 0xFEFFFFFFu;   // shared::cluster address of the pair leader's copy
+      for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+        int m_blk, n_blk; tile_coords(tile, g, m_blk, n_blk);
+        const int a_row = (m_blk * CG + (int)cta_rank) * BM;
+        const int b_row = n_blk * BN + (int)cta_rank * C_::B_ROWS;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(&full[stage], C_::STAGE_BYTES);
+            tma_load_2d(smA + stage * C_::A_BYTES, &tmA, &full[stage], kb * BK, a_row);
+            tma_load_2d(smB + stage * C_::B_BYTES, &tmB, &full[stage], kb * BK, b_row);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C_::STAGE_BYTES);
+            else        mbar_arrive_cluster(&full[stage], 0);
+            const uint32_t bar = smem_u32(&full[stage]) & full_leader_mask;
+            tma_load_2d_2sm(smA + stage * C_::A_BYTES, &tmA, bar, kb * BK, a_row);
+            tma_load_2d_2sm(smB + stage * C_::B_BYTES, &tmB, bar, kb * BK, b_row);
+          }
+          if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (pair leader only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_k_sw128(smem_u32(smA + stage * C_::A_BYTES));
+          const uint64_t bd = umma_desc_k_sw128(smem_u32(smB + stage * C_::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)   // +32 B per UMMA_K inside the 128B swizzle row
+            umma_ss<CG>(d_tmem, ad + (uint64_t)(k * UK * 2 / 16), bd + (uint64_t)(k * UK * 2 / 16), idesc, (kb | k) != 0);
+          if constexpr (CG == 1) umma_commit(&empty[stage]); else umma_commit_2sm(&empty[stage], 0b11);
+          if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 1) umma_commit(&tfull[acc]); else umma_commit_2sm(&tfull[acc], 0b11);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------ epilogue: TMEM -> registers -> HBM
+    const int q = warp - EPI_WARP0;                      // == warp % 4: the TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      int m_blk, n_blk; tile_coords(tile, g, m_blk, n_blk);
+      const long long row = (long long)(m_blk * CG + (int)cta_rank) * BM + q * 32 + lane;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
+      if constexpr (EPI == EVO_EPI_GELU_GATE) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 32) {
+          uint32_t r1[32], r2[32];
+          tmem_ld_32x32(t0 + c, r1);
+          tmem_ld_32x32(t0 + BN / 2 + c, r2);
+          tmem_ld_wait();
+          if (row < g.M) store_chunk<EPI>(g, row, n_blk * (BN / 2) + c, r1, r2);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r1[32];
+          tmem_ld_32x32(t0 + c, r1);
+          tmem_ld_wait();
+          if (row < g.M) store_chunk<EPI>(g, row, n_blk * BN + c, r1, r1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if constexpr (CG == 1) mbar_arrive(&tempty[acc]); else mbar_arrive_cluster(&tempty[acc], 0); }
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  __syncwarp();            // single-lane roles rejoin their warp before the aligned barriers
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+template <int CG, int EPI>
+int launch(const evo_gemm_params* p, cudaStream_t st) {
+  using C_ = Cfg<CG>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda * 2, BK, BM, true))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, p->W, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->K * 2, BK, C_::B_ROWS, true))) return rc;
+  GemmArgs g;
+  g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
+  g.M = p->M; g.N = p->N; g.K = p->K;
+  g.m_blocks = (int)((p->M + BM * CG - 1) / (BM * CG));
+  g.n_blocks = (int)(p->N / BN);
+  g.group_m = CG == 1 ? 16 : 8;
+  static bool attr_done = false;
+  auto kern = gemm_tcgen05_kernel<CG, EPI>;
+  if (!attr_done) {
+    EVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+    attr_done = true;
+  }
+  int sms = device_sm_count();
+  int n_tiles = g.m_blocks * g.n_blocks;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (CG == 2) {
+    int pairs = min(n_tiles, sms / 2);
+    cfg.gridDim = dim3(pairs * 2);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(min(n_tiles, sms));
+  }
+  EVO_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g));
+  return check_launch("evo_gemm");
+}
+
+template <int CG>
+int dispatch_epi(const evo_gemm_params* p, cudaStream_t st) {
+  switch (p->epilogue) {
+    case EVO_EPI_NONE: return launch<CG, EVO_EPI_NONE>(p, st);
+    case EVO_EPI_BIAS: return launch<CG, EVO_EPI_BIAS>(p, st);
+    case EVO_EPI_BIAS_RESID: return launch<CG, EVO_EPI_BIAS_RESID>(p, st);
+    case EVO_EPI_RESID: return launch<CG, EVO_EPI_RESID>(p, st);
+    case EVO_EPI_GELU_GATE: return launch<CG, EVO_EPI_GELU_GATE>(p, st);
+  }
+  set_error("evo_gemm: unknown epilogue %d", p->epilogue);
+  return -1;
+}
+
+}  // namespace
+
+extern "C" int evo_gemm(const evo_gemm_params* p, void* stream) {
+  EVO_REQUIRE(p->M >= 0 && p->N > 0 && p->K > 0, "evo_gemm: bad shape");
+  EVO_REQUIRE(p->K % BK == 0, "evo_gemm: K (%lld) must be a multiple of %d", (long long)p->K, BK);
+  EVO_REQUIRE(p->N % BN == 0, "evo_gemm: N (%lld) must be a multiple of %d (pack weights at load time)", (long long)p->N, BN);
+  EVO_REQUIRE(p->lda % 8 == 0 && p->ldc % 8 == 0, "evo_gemm: lda/ldc must be multiples of 8 elements");
+  EVO_REQUIRE(((uintptr_t)p->A % 16) == 0 && ((uintptr_t)p->W % 16) == 0 && ((uintptr_t)p->C % 16) == 0, "evo_gemm: pointers must be 16-byte aligned");
+  if (p->epilogue == EVO_EPI_BIAS || p->epilogue == EVO_EPI_BIAS_RESID) EVO_REQUIRE(p->bias != nullptr, "evo_gemm: bias epilogue without bias");
+  if (p->epilogue == EVO_EPI_RESID || p->epilogue == EVO_EPI_BIAS_RESID)
+    EVO_REQUIRE(p->residual != nullptr && p->ldr % 8 == 0 && ((uintptr_t)p->residual % 16) == 0, "evo_gemm: residual epilogue without a valid residual");
+  if (p->M == 0) return 0;
+  if (p->variant == 1) return dispatch_epi<1>(p, (cudaStream_t)stream);
+  return dispatch_epi<2>(p, (cudaStream_t)stream);
+}

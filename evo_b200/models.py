@@ -1,0 +1,80 @@
+"""`Evo` front door and checkpoint ingest: the reference's evo/models.py (Evo :21-62,
+load_checkpoint :73-152) re-expressed for the evo_b200 engine.  Checkpoint key names after
+the 'backbone.' strip, the tied unembed, strict loading and the bf16-except-poles/residues
+dtype policy are the contract (evo/models.py:124-148)."""
+from __future__ import annotations
+
+import json
+import os
+from typing import Optional
+
+import torch
+import yaml
+
+from .configs import MODEL_NAMES, MODELS, get_config
+from .stripedhyena import StripedHyena, dotdict
+from .tokenizer import CharLevelTokenizer
+
+HF_MODEL_NAME_MAP = {name: spec[1] for name, spec in MODELS.items()}
+
+
+def _read_safetensors(model_dir: str) -> dict:
+    from safetensors.torch import load_file
+    index = os.path.join(model_dir, "model.safetensors.index.json")
+    single = os.path.join(model_dir, "model.safetensors")
+    if os.path.exists(index):
+        with open(index) as f:
+            shards = sorted(set(json.load(f)["weight_map"].values()))
+        tensors = {}
+        for shard in shards:
+            tensors.update(load_file(os.path.join(model_dir, shard)))
+        return tensors
+    if os.path.exists(single):
+        return load_file(single)
+    raise FileNotFoundError(f"No safetensors files found in {model_dir}. Expected model.safetensors.index.json or model.safetensors.")
+
+
+def load_checkpoint(model_name: str = "evo-1-8k-base", config_path: Optional[str] = None, device: str = None,
+                    model_dir: Optional[str] = None, random_init: bool = False, seed: int = 0, *args, **kwargs):
+    """HF snapshot -> safetensors -> StripedHyena on `device`.
+
+    model_dir: use an already-downloaded snapshot directory instead of huggingface_hub.
+    random_init: skip the checkpoint (benchmarks / tests on boxes without network) and keep the
+    constructor's random initialisation, seeded."""
+    if config_path is not None and os.path.exists(config_path):
+        with open(config_path) as f:
+            cfg = yaml.safe_load(f)
+    else:
+        cfg = get_config(model_name)
+    cfg = dotdict(cfg)
+
+    if random_init:
+        torch.manual_seed(seed)
+        model = StripedHyena(cfg)
+    else:
+        if model_dir is None:
+            from huggingface_hub import snapshot_download
+            _, repo, revision = MODELS[model_name]
+            model_dir = snapshot_download(repo, revision=revision)
+        state = {}
+        for key, value in _read_safetensors(model_dir).items():
+            state[key[len("backbone."):] if key.startswith("backbone.") else key] = value
+        if "unembed.weight" not in state and "embedding_layer.weight" in state:
+            state["unembed.weight"] = state["embedding_layer.weight"]
+        model = StripedHyena(cfg)
+        model.load_state_dict(state, strict=True)
+    model.to_bfloat16_except_poles_residues()
+    if device is not None:
+        model = model.to(device)
+    return model
+
+
+class Evo:
+    """Evo('evo-1-8k-base') -> .model (StripedHyena protocol), .tokenizer."""
+
+    def __init__(self, model_name: str = "evo-1-8k-base", device: str = None, **load_kwargs):
+        if model_name not in MODEL_NAMES:
+            raise ValueError(f"Invalid model name {model_name}. Should be one of: {', '.join(MODEL_NAMES)}.")
+        self.device = device
+        self.model = load_checkpoint(model_name=model_name, device=device, **load_kwargs)
+        self.tokenizer = CharLevelTokenizer(512)

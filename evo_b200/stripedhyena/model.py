@@ -1,0 +1,364 @@
+"""`StripedHyena` with the object protocol evo-design/evo relies on, executed by libevo_b200.so.
+
+Boundary obligations, each pinned by a reference call site:
+  StripedHyena(cfg)                                  evo/models.py:146
+  .load_state_dict(sd, strict=True) with HF names    evo/models.py:124-147
+  .to_bfloat16_except_poles_residues(); .to(device)  evo/models.py:148-150
+  model(ids) -> (logits, None)                       evo/scoring.py:81,116
+  model(x, inference_params_dict=d) -> (logits, d)   evo/generation.py:152
+  model.initialize_inference_params()                evo/generation.py:117
+
+The module tree only exists to carry parameters under the checkpoint's key names; `forward`
+never calls a torch op on activations.  torch supplies device memory and the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID, AttnParams, GemmParams,
+                    HyenaParams, check, ptr)
+from .cache import InferenceParams, RecurrentInferenceParams
+
+# kernel variants (see include/evo_b200.h); overridable for experiments
+GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "0"))
+ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "0"))
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------- parameter carriers
+class _Scale(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.scale = nn.Parameter(torch.ones(dim))
+
+
+class _Linear(nn.Module):
+    def __init__(self, fan_in, fan_out, bias):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(fan_out, fan_in).normal_(0.0, 1.0 / math.sqrt(fan_in)))
+        self.bias = nn.Parameter(torch.zeros(fan_out)) if bias else None
+
+
+class _GatedMLP(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        d = cfg.hidden_size
+        mult = cfg.get("inner_size_multiple_of", 64) * (cfg.get("model_parallel_size") or 1)
+        inner = mult * ((int(2 * d * 4 / 3) + mult - 1) // mult)
+        if cfg.get("inner_mlp_size") is not None:
+            inner = cfg.get("inner_mlp_size")
+        if (cfg.get("mlp_activation") or "silu") != "gelu":
+            raise NotImplementedError("evo_b200 implements the Evo configs' exact-erf GELU gate only")
+        self.inner = inner
+        self.l1 = _Linear(d, inner, False)
+        self.l2 = _Linear(d, inner, False)
+        self.l3 = _Linear(inner, d, False)
+
+
+class _HyenaFilter(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        d, s, k = cfg.hidden_size, cfg.state_size, cfg.short_filter_length
+        if k != 3 or s != 8:
+            raise NotImplementedError("kernels are specialised for short_filter_length=3, state_size=8 (the Evo configs)")
+        if (cfg.get("hyena_filter_groups") or 1) != 1:
+            raise NotImplementedError("hyena_filter_groups != 1")
+        self.short_filter_weight = nn.Parameter(torch.randn(3 * d, 1, k) * 0.3)
+        self.short_filter_bias = nn.Parameter(torch.randn(3 * d) * 0.1)
+        self.D = nn.Parameter(torch.zeros(d))
+        mag = 0.5 + 0.45 * torch.rand(d, s, 1)
+        ang = (torch.rand(d, s, 1) * 2 - 1) * math.pi
+        self.poles = nn.Parameter(torch.stack([mag * torch.cos(ang), mag * torch.sin(ang)], dim=-1))
+        self.residues = nn.Parameter(torch.randn(d, s, 1, 2) * 0.3)
+
+
+class _Rotary(nn.Module):
+    def __init__(self, head_dim, base):
+        super().__init__()
+        self.register_buffer("inv_freq", 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim)))
+
+
+class _MHA(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        d = cfg.hidden_size
+        if (cfg.get("proj_groups") or 1) != 1:
+            raise NotImplementedError("proj_groups != 1 (GQA) is not an Evo configuration")
+        self.Wqkv = _Linear(d, 3 * d, bool(cfg.get("qkv_proj_bias", True)))
+        self.out_proj = _Linear(d, d, bool(cfg.get("mha_out_proj_bias", True)))
+        self.rotary_emb = _Rotary(d // cfg.num_attention_heads, cfg.get("rotary_emb_base") or 10000)
+
+
+class _HyenaBlock(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        d = cfg.hidden_size
+        self.pre_norm, self.post_norm = _Scale(d), _Scale(d)
+        self.filter = _HyenaFilter(cfg)
+        self.projections = _Linear(d, 3 * d, True)
+        self.out_filter_dense = _Linear(d, d, True)
+        self.mlp = _GatedMLP(cfg)
+
+
+class _AttentionBlock(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        d = cfg.hidden_size
+        self.pre_norm, self.post_norm = _Scale(d), _Scale(d)
+        self.inner_mha_cls = _MHA(cfg)
+        self.mlp = _GatedMLP(cfg)
+
+
+class _Embedding(nn.Module):
+    def __init__(self, vocab, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(vocab, dim) * (2.5 / math.sqrt(dim)))
+
+
+# ----------------------------------------------------------------------------- the model
+class StripedHyena(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        d = config.hidden_size
+        self.embedding_layer = _Embedding(config.vocab_size, d)
+        self.norm = _Scale(d) if config.get("final_norm", True) else None
+        self.unembed = self.embedding_layer if config.tie_embeddings else _Embedding(config.vocab_size, d)
+        attn = set(config.attn_layer_idxs or [])
+        self.blocks = nn.ModuleList(
+            _AttentionBlock(config) if i in attn else _HyenaBlock(config) for i in range(config.num_layers))
+        self._attn_idxs = attn
+        self._packed = None
+        self._rope = None
+        self.gemm_variant = GEMM_VARIANT
+        self.attn_variant = ATTN_VARIANT
+
+    # ---- reference API ------------------------------------------------------------------
+    def to_bfloat16_except_poles_residues(self):
+        for name, p in self.named_parameters():
+            if "poles" not in name and "residues" not in name:
+                p.data = p.data.to(torch.bfloat16)
+        self._packed = None
+        return self
+
+    def initialize_inference_params(self):
+        return {
+            "mha": InferenceParams(max_seqlen=self.config.get("max_seqlen") or 8192,
+                                   max_batch_size=self.config.get("max_batch_size") or 1, seqlen_offset=0),
+            "hyena": RecurrentInferenceParams(fir_filter_length=self.config.short_filter_length,
+                                              state_dim=self.config.state_size, seqlen_offset=0),
+        }
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._packed = None
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._packed = None
+        self._rope = None
+        return out
+
+    # ---- weight packing (once per load / move) ---------------------------------------------
+    def _ensure_packed(self):
+        if self._packed is not None:
+            return self._packed
+        dev = self.embedding_layer.weight.device
+        if dev.type != "cuda":
+            raise _lib.EvoError("evo_b200 runs on CUDA (sm_100a) only: move the model with .to('cuda:N'); there is no CPU path")
+        for name, p in self.named_parameters():
+            want = torch.float32 if ("poles" in name or "residues" in name) else torch.bfloat16
+            if p.dtype != want:
+                raise _lib.EvoError(f"parameter {name} is {p.dtype}; call to_bfloat16_except_poles_residues() (evo/models.py:148)")
+            if p.device != dev:
+                raise _lib.EvoError(f"parameter {name} is on {p.device}, expected {dev}")
+        packed = {}
+        for i, blk in enumerate(self.blocks):
+            inner = blk.mlp.inner
+            ipad = _round_up(inner, 128)
+            with torch.no_grad():
+                l1 = F.pad(blk.mlp.l1.weight.data, (0, 0, 0, ipad - inner)).view(ipad // 128, 1, 128, -1)
+                l2 = F.pad(blk.mlp.l2.weight.data, (0, 0, 0, ipad - inner)).view(ipad // 128, 1, 128, -1)
+                w12 = torch.cat([l1, l2], dim=1).reshape(2 * ipad, -1).contiguous()       # [l1 | l2] per 256-row tile
+                w3 = F.pad(blk.mlp.l3.weight.data, (0, ipad - inner)).contiguous()          # zero K-padding
+            packed[i] = {"w12": w12, "w3": w3, "ipad": ipad}
+        hd = self.config.hidden_size // self.config.num_attention_heads
+        base = self.config.get("rotary_emb_base") or 10000
+        # flash_attn recomputes inv_freq in fp32 when the buffer is not fp32 (layers/rotary.py:386-401)
+        packed["inv_freq"] = (1.0 / (base ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))).to(dev)
+        self._packed = packed
+        return packed
+
+    # ---- thin wrappers over the C ABI ------------------------------------------------------------
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None):
+        p = GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=ldc or N,
+                       bias=bias.data_ptr() if bias is not None else None,
+                       residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
+                       M=M, N=N, K=K, epilogue=epi, variant=self.gemm_variant)
+        check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm")
+
+    def _rmsnorm(self, x, scale, out, rows):
+        check(_lib.lib().evo_rmsnorm(ptr(x), ptr(scale), ptr(out), rows, self.config.hidden_size,
+                                     float(self.config.eps), self._stream()), "evo_rmsnorm")
+
+    def _rope_tables(self, n_pos, dev):
+        if self._rope is None or self._rope[0].shape[0] < n_pos:
+            hd2 = self.config.hidden_size // self.config.num_attention_heads // 2
+            scaling = float(self.config.get("rotary_emb_scaling_factor") or 1.0) if self.config.get("use_interpolated_rotary_pos_emb") else 1.0
+            n = max(n_pos, 2048)
+            cos = torch.empty(n, hd2, dtype=torch.bfloat16, device=dev)
+            sin = torch.empty_like(cos)
+            check(_lib.lib().evo_rope_tables(ptr(cos), ptr(sin), ptr(self._packed["inv_freq"]), 0, n, hd2, scaling, self._stream()), "evo_rope_tables")
+            self._rope = (cos, sin)
+        return self._rope
+
+    def _mlp_residual(self, i, blk, u, M):
+        """out = l3(gelu(l1 n) * l2 n) + u with n = post_norm(u); returns a new (M, D) tensor."""
+        d = self.config.hidden_size
+        pk = self._packed[i]
+        xn = torch.empty_like(u)
+        self._rmsnorm(u, blk.post_norm.scale, xn, M)
+        g = torch.empty(M, pk["ipad"], dtype=torch.bfloat16, device=u.device)
+        self._gemm(xn, pk["w12"], g, M, 2 * pk["ipad"], d, EPI_GELU_GATE, ldc=pk["ipad"])
+        out = xn  # reuse
+        self._gemm(g, pk["w3"], out, M, d, pk["ipad"], EPI_RESID, resid=u)
+        return out
+
+    def _hyena_block(self, i, blk, u, B, L, ip: Optional[RecurrentInferenceParams]):
+        cfg = self.config
+        d, H = cfg.hidden_size, cfg.num_attention_heads
+        M = B * L
+        dev = u.device
+        f = blk.filter
+        xn = torch.empty_like(u)
+        self._rmsnorm(u, blk.pre_norm.scale, xn, M)
+        z = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
+        self._gemm(xn, blk.projections.weight, z, M, 3 * d, d, EPI_BIAS, bias=blk.projections.bias)
+        y = xn  # (M, D) buffer reuse
+        lib = _lib.lib()
+        have_state = ip is not None and i in ip.fir_state_dict
+        if have_state and L == 1:
+            st = ip.state_dict[i]
+            if not st.is_contiguous():
+                st = st.contiguous(); ip.state_dict[i] = st
+            fs = ip.fir_state_dict[i]
+            if not fs.is_contiguous():
+                fs = fs.contiguous(); ip.fir_state_dict[i] = fs
+            check(lib.evo_hyena_step(ptr(z), ptr(y), ptr(fs), ptr(torch.view_as_real(st)), ptr(f.short_filter_weight),
+                                     ptr(f.short_filter_bias), ptr(f.D), ptr(f.poles), ptr(f.residues),
+                                     B, d, cfg.state_size, H, self._stream()), "evo_hyena_step")
+        else:
+            hp = HyenaParams(z=z.data_ptr(), y=y.data_ptr(), fir_w=f.short_filter_weight.data_ptr(), fir_b=f.short_filter_bias.data_ptr(),
+                             Dskip=f.D.data_ptr(), poles=f.poles.data_ptr(), residues=f.residues.data_ptr(),
+                             B=B, L=L, D=d, S=cfg.state_size, nheads=H, force_segments=0, state_only=0)
+            keep = []
+            if have_state:  # continued prefill: history = stored states
+                halo = ip.fir_state_dict[i].permute(0, 2, 1).contiguous()
+                sin_ = torch.view_as_real(ip.state_dict[i].contiguous()).contiguous()
+                hp.halo, hp.state_in = halo.data_ptr(), sin_.data_ptr()
+                keep += [halo, sin_]
+            if ip is not None:
+                st_out = torch.empty(B, d, cfg.state_size, 2, dtype=torch.float32, device=dev)
+                fs_out = torch.empty(B, 3 * d, 2, dtype=torch.bfloat16, device=dev)
+                hp.state_out, hp.fir_state_out = st_out.data_ptr(), fs_out.data_ptr()
+            ws_bytes = lib.evo_hyena_fwd_workspace(C.byref(hp))
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), ws_bytes, self._stream()), "evo_hyena_fwd")
+            if ip is not None:
+                ip.state_dict[i] = torch.view_as_complex(st_out)
+                ip.fir_state_dict[i] = fs_out
+        u2 = torch.empty_like(u)
+        self._gemm(y, blk.out_filter_dense.weight, u2, M, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u)
+        return self._mlp_residual(i, blk, u2, M)
+
+    def _attention_block(self, i, blk, u, B, L, ip: Optional[InferenceParams]):
+        cfg = self.config
+        d, H = cfg.hidden_size, cfg.num_attention_heads
+        hd = d // H
+        M = B * L
+        dev = u.device
+        mha = blk.inner_mha_cls
+        lib = _lib.lib()
+        xn = torch.empty_like(u)
+        self._rmsnorm(u, blk.pre_norm.scale, xn, M)
+        qkv = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
+        self._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
+        off = int(ip.seqlen_offset) if ip is not None else 0
+        cos, sin = self._rope_tables(off + L, dev)
+        hd2 = hd // 2
+        check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + off * hd2 * 2), C.c_void_p(sin.data_ptr() + off * hd2 * 2),
+                                B, L, H, hd, self._stream()), "evo_rotary_qk")
+        ctx = xn  # reuse
+        ap = AttnParams(out=ctx.data_ptr(), B=B, Lq=L, H=H, hd=hd, q_pos0=off, softmax_scale=1.0 / math.sqrt(hd))
+        ap.q, ap.q_tok_stride, ap.q_batch_stride = qkv.data_ptr(), 3 * d, L * 3 * d
+        if ip is None:
+            ap.k, ap.v = qkv.data_ptr() + d * 2, qkv.data_ptr() + 2 * d * 2
+            ap.kv_tok_stride, ap.kv_batch_stride, ap.Lk = 3 * d, L * 3 * d, L
+        else:
+            if i not in ip.key_value_memory_dict:  # flash_attn/modules/mha.py:344-353 (zeros instead of empty: quirk Q1)
+                ip.key_value_memory_dict[i] = torch.zeros(ip.max_batch_size, ip.max_seqlen, 2, H, hd, dtype=torch.bfloat16, device=dev)
+            cache = ip.key_value_memory_dict[i]
+            if B > cache.shape[0] or off + L > cache.shape[1]:
+                raise _lib.EvoError(f"KV cache too small: batch {B} > {cache.shape[0]} or length {off + L} > {cache.shape[1]} (mha.py:366-367)")
+            check(lib.evo_kv_append(ptr(qkv), ptr(cache), B, L, H, hd, off, cache.shape[1], self._stream()), "evo_kv_append")
+            ap.k, ap.v = cache.data_ptr(), cache.data_ptr() + d * 2
+            ap.kv_tok_stride, ap.kv_batch_stride, ap.Lk = 2 * d, cache.shape[1] * 2 * d, off + L
+        ws_bytes = lib.evo_attn_fwd_workspace(C.byref(ap), self.attn_variant)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        check(lib.evo_attn_fwd_ws(C.byref(ap), self.attn_variant, ptr(ws), ws_bytes, self._stream()), "evo_attn_fwd")
+        u2 = torch.empty_like(u)
+        self._gemm(ctx, mha.out_proj.weight, u2, M, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID,
+                   bias=mha.out_proj.bias, resid=u)
+        return self._mlp_residual(i, blk, u2, M)
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def forward(self, x, inference_params_dict=None, padding_mask=None):
+        if padding_mask is not None:
+            raise NotImplementedError("padding_mask is never passed by evo (evo/scoring.py:81); not implemented")
+        if x.dim() != 2:
+            raise ValueError("input ids must be (batch, length)")
+        if x.dtype not in (torch.int32, torch.int64):
+            raise TypeError("input ids must be int32 or int64")
+        self._ensure_packed()
+        dev = self.embedding_layer.weight.device
+        if x.device != dev:
+            raise _lib.EvoError(f"input ids on {x.device}, model on {dev}")
+        x = x.contiguous()
+        B, L = x.shape
+        M = B * L
+        d = self.config.hidden_size
+        V = self.config.vocab_size
+        with torch.cuda.device(dev), torch.no_grad():
+            u = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
+            check(_lib.lib().evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u),
+                                       M, d, V, self._stream()), "evo_embed")
+            for i, blk in enumerate(self.blocks):
+                if i in self._attn_idxs:
+                    ip = inference_params_dict["mha"] if inference_params_dict is not None else None
+                    u = self._attention_block(i, blk, u, B, L, ip)
+                else:
+                    ip = inference_params_dict["hyena"] if inference_params_dict is not None else None
+                    u = self._hyena_block(i, blk, u, B, L, ip)
+            if self.norm is not None:
+                xn = torch.empty_like(u)
+                self._rmsnorm(u, self.norm.scale, xn, M)
+                u = xn
+            logits = torch.empty(M, V, dtype=torch.bfloat16, device=dev)
+            self._gemm(u, self.unembed.weight, logits, M, V, d, EPI_NONE)
+        return logits.view(B, L, V), inference_params_dict

@@ -1,0 +1,152 @@
+/* evo_b200 — C ABI of the B200-native StripedHyena forward engine.
+ *
+ * The reference (evo-design/evo) has no FFI: its boundary is the Python duck-type
+ * of stripedhyena.model.StripedHyena (evo/models.py:141-150, evo/scoring.py:81,
+ * evo/generation.py:117,152).  Everything that object computes is executed by the
+ * entry points below; evo_b200/stripedhyena/model.py binds them with ctypes and
+ * mirrors the Python protocol on top.  Each entry point cites the reference
+ * operation it replaces (names inside stripedhyena==0.2.2 / flash_attn, which the
+ * reference pins in requirements.txt:1 and README.md:47-48).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer owned by the caller (a torch tensor);
+ *     the library never allocates device memory except a small per-device cache
+ *     (TMA descriptors / cuBLASLt handle for the test comparator);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *   - bf16 tensors are row-major with the innermost dimension contiguous;
+ *   - return value 0 = ok, negative = error; evo_last_error() has the message;
+ *   - no exceptions cross the boundary, no torch types appear in signatures.
+ */
+#ifndef EVO_B200_H
+#define EVO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* evo_last_error(void);
+int evo_abi_version(void);
+/* #launches of evo_b200 kernels since the last evo_reset_launch_count() (bench: gpu_launches) */
+int64_t evo_launch_count(void);
+void evo_reset_launch_count(void);
+
+/* ---- embedding gather: VocabParallelEmbedding.embed (evo/models.py:136 pins the key) ----
+ * ids: int32 or int64 (ids_are_i64), n tokens; table (vocab, D) bf16; out (n, D) bf16. */
+int evo_embed(const void* ids, int ids_are_i64, const void* table, void* out,
+              int64_t n_tokens, int D, int vocab, void* stream);
+
+/* ---- RMSNorm, non-flash branch of stripedhyena layers.RMSNorm.forward:
+ * y = scale * x / (||x||_2 * D^-1/2 + eps), every intermediate rounded to bf16 as the
+ * reference's bf16 tensor ops do.  x,out (rows, D) bf16; scale (D) bf16. */
+int evo_rmsnorm(const void* x, const void* scale, void* out, int64_t rows, int D, float eps, void* stream);
+
+/* ---- tensor-core linear layers (nn.Linear / ParallelGatedMLP / unembed) ----
+ * C[M,N] = epilogue(A[M,K] . W[N,K]^T), bf16 in, fp32 accumulate (tcgen05, TMEM), bf16 out.
+ * Requirements: K % 64 == 0, N % 256 == 0 (weights are re-packed once at load time,
+ * see evo_b200/stripedhyena/model.py), lda/ldc/ldr in elements. */
+enum {
+  EVO_EPI_NONE = 0,       /* C = bf16(acc)                                              */
+  EVO_EPI_BIAS = 1,       /* C = bf16(acc + bias[n])                nn.Linear(bias=True) */
+  EVO_EPI_BIAS_RESID = 2, /* C = bf16(bf16(acc + bias[n]) + R[m,n]) out_filter_dense(z)+u, out_proj(ctx)+u */
+  EVO_EPI_RESID = 3,      /* C = bf16(bf16(acc) + R[m,n])           l3(...) + u           */
+  EVO_EPI_GELU_GATE = 4   /* W rows interleaved in 128-row groups [l1 | l2]; C[M,N/2] =
+                             bf16(gelu(bf16(acc1)) * bf16(acc2))    act(l1 x) * l2 x      */
+};
+typedef struct {
+  const void* A; int64_t lda;
+  const void* W;                 /* (N, K) row-major */
+  void* C; int64_t ldc;
+  const void* bias;              /* (N) bf16 or NULL */
+  const void* residual; int64_t ldr;
+  int64_t M, N, K;
+  int epilogue;
+  int variant;                   /* 0 = default (2-CTA pairs); 1 = single-CTA tiles */
+} evo_gemm_params;
+int evo_gemm(const evo_gemm_params* p, void* stream);
+/* test comparator only (cuBLASLt, plain C = A.W^T [+bias]); never on the product path */
+int evo_gemm_cublaslt_reference(const evo_gemm_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- fused Hyena operator: HyenaInferenceEngine.parallel_fir + ParallelHyenaFilter.
+ * compute_filter + parallel_iir (+ prefill_via_modal_fft) of stripedhyena 0.2.2, as one
+ * modal scan.  z (B, L, 3D) bf16 -> y (B, L, D) bf16.
+ *   fir_w (3D, 3) bf16 taps [t-2, t-1, t]; fir_b (3D) bf16; Dskip (D) bf16;
+ *   poles, residues (D, S, 2) fp32 (re, im), S == 8; nheads: column-split head count.
+ * Optional (NULL to skip):
+ *   halo (B, 2, 3D) bf16: the two z rows preceding row 0 (sequence-sharded rank > 0, or
+ *        a continued prefill); zero history otherwise.
+ *   state_in (B, D, S, 2) fp32: modal state entering row 0.
+ *   state_out (B, D, S, 2) fp32: modal state after the last row (== inference_params.
+ *        state_dict[layer] of the reference, complex64).
+ *   fir_state_out (B, 3D, 2) bf16: last two z rows (== fir_state_dict[layer]).
+ * workspace: evo_hyena_fwd_workspace() bytes (segment carries when L is split). */
+typedef struct {
+  const void* z; void* y;
+  const void* fir_w; const void* fir_b; const void* Dskip;
+  const float* poles; const float* residues;
+  int B; int64_t L; int D; int S; int nheads;
+  const void* halo; const float* state_in;
+  float* state_out; void* fir_state_out;
+  int force_segments;            /* 0 = auto; >0 forces the number of L segments (tests) */
+  int state_only;                /* 1 = compute state_out only (sequence-parallel carry pass); y may be NULL */
+} evo_hyena_params;
+size_t evo_hyena_fwd_workspace(const evo_hyena_params* p);
+int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* decode step: engine.step_fir + step_iir.  u (B, 3D) bf16 -> y (B, D) bf16;
+ * fir_state (B, 3D, 2) bf16 and state (B, D, S, 2) fp32 are updated in place. */
+int evo_hyena_step(const void* u, void* y, void* fir_state, float* state,
+                   const void* fir_w, const void* fir_b, const void* Dskip,
+                   const float* poles, const float* residues,
+                   int B, int D, int S, int nheads, void* stream);
+
+/* combine per-rank end states into the state entering rank `rank`'s shard:
+ * S_in = sum_{q<rank} p^{(rank-1-q)*seg_len} * ends[q].  ends (nranks, B, D, S, 2) fp32. */
+int evo_hyena_combine_states(const float* ends, float* state_in, const float* poles,
+                             int rank, int nranks, int64_t seg_len, int B, int D, int S, void* stream);
+
+/* ---- rotary tables + application (flash_attn layers/rotary.py:382-416,
+ * ops/triton/rotary.py; stripedhyena LinearlyScaledRotaryEmbedding for 131k) ----
+ * cos/sin (n_pos, hd/2) bf16 for positions pos0 .. pos0+n_pos-1, angle = (pos/scaling) * inv_freq[i]. */
+int evo_rope_tables(void* cos_out, void* sin_out, const float* inv_freq, int64_t pos0, int64_t n_pos,
+                    int half_dim, float scaling_factor, void* stream);
+/* in-place NeoX rotary on q and k of qkv (B, L, 3, H, 128) bf16; cos/sin rows index the
+ * position of row l directly (caller offsets the table for decode). */
+int evo_rotary_qk(void* qkv, const void* cos, const void* sin, int B, int64_t L, int H, int hd, void* stream);
+
+/* ---- causal attention core: flash_attn_qkvpacked_func (mha.py:122) ----
+ * q: (B, Lq, H, 128) with row stride q_stride elements between tokens; k, v likewise over Lk
+ * keys; query i attends keys j <= q_pos0 + i.  out (B, Lq, H*128) bf16 contiguous. */
+typedef struct {
+  const void* q; const void* k; const void* v; void* out;
+  int64_t q_tok_stride, kv_tok_stride;     /* elements between consecutive tokens */
+  int64_t q_batch_stride, kv_batch_stride; /* elements between batches */
+  int B; int64_t Lq, Lk; int H; int hd;
+  int64_t q_pos0;
+  float softmax_scale;
+} evo_attn_params;
+/* variant 0: V is transposed into the workspace first and consumed as a K-major operand;
+ * variant 1: V is consumed in place as an MN-major operand (no workspace). */
+size_t evo_attn_fwd_workspace(const evo_attn_params* p, int variant);
+int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* workspace, size_t workspace_bytes, void* stream);
+/* plain CUDA-core comparator for tests; never on the product path */
+int evo_attn_fwd_simple(const evo_attn_params* p, void* stream);
+
+/* append k,v of qkv (B, L, 3, H, hd) at rows [pos0, pos0+L) of the KV cache
+ * (max_B, max_seqlen, 2, H, hd) bf16 — MHA._update_kv_cache (mha.py:344-370). */
+int evo_kv_append(const void* qkv, void* cache, int B, int64_t L, int H, int hd,
+                  int64_t pos0, int64_t max_seqlen, void* stream);
+
+/* ---- elementwise glue kept for completeness / tests ---- */
+int evo_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* ---- scoring epilogue: evo/scoring.py:36-59 logits_to_logprobs ----
+ * logits (rows, V) bf16; targets (rows) int64 (-1 = skip -> 0); out (rows) fp32 =
+ * log_softmax(logits)[target], fp32 statistics. */
+int evo_logprobs(const void* logits, const int64_t* targets, float* out, int64_t rows, int V, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+"""Host-side logic that needs no GPU: tokenizer, batching, scoring math, sampling, config,
+the StripedHyena parameter tree / strict loading, and the generation loop's state protocol
+(driven with a CPU stand-in model)."""
+import numpy as np
+import pytest
+import torch
+
+import evo_b200
+from evo_b200 import CharLevelTokenizer, logits_to_logprobs, prepare_batch
+from evo_b200.configs import MODEL_NAMES, get_config
+from evo_b200.generation import Generator
+from evo_b200.stripedhyena import StripedHyena, dotdict, sample
+from oracle import stripedhyena_oracle as O
+
+
+def test_tokenizer_roundtrip():
+    tok = CharLevelTokenizer(512)
+    assert tok.tokenize("ACGT") == [65, 67, 71, 84]
+    assert (tok.eod_id, tok.eos_id, tok.pad_id, tok.vocab_size) == (0, 0, 1, 512)
+    assert tok.detokenize([65, 67, 71, 84]) == "ACGT"
+    assert tok.detokenize([0, 1, 31]) == "   "          # clamped to >= 32 (evo/tokenizer.py:22-23)
+    assert tok.detokenize_batch(torch.tensor([[65, 67], [71, 84]])) == ["AC", "GT"]
+    assert tok.tokenize_batch(["A", "CG"]) == [[65], [67, 71]]
+
+
+def test_prepare_batch_pads_and_prepends_bos():
+    tok = CharLevelTokenizer(512)
+    ids, lens = prepare_batch(["ACGT", "AC"], tok, prepend_bos=True, device="cpu")
+    assert lens == [4, 2] and ids.dtype == torch.long
+    assert ids.tolist() == [[0, 65, 67, 71, 84], [0, 65, 67, 1, 1]]
+    ids, _ = prepare_batch(["ACGT"], tok, prepend_bos=False, device="cpu")
+    assert ids.tolist() == [[65, 67, 71, 84]]
+
+
+def test_logits_to_logprobs_alignment():
+    torch.manual_seed(0)
+    logits = torch.randn(2, 5, 8)
+    ids = torch.randint(0, 8, (2, 5))
+    lp = logits_to_logprobs(logits, ids, trim_bos=True)
+    ref = torch.log_softmax(logits, -1)
+    assert lp.shape == (2, 4)
+    for b in range(2):
+        for t in range(4):
+            assert lp[b, t] == ref[b, t, ids[b, t + 1]]
+    assert logits_to_logprobs(logits, ids, trim_bos=False).shape == (2, 5)
+
+
+def test_sample_matches_oracle_semantics():
+    lg = torch.randn(6, 512)
+    assert torch.equal(sample(lg, top_k=1), lg.argmax(-1))
+    assert torch.equal(sample(lg[:, None, :], top_k=1), lg.argmax(-1))
+    torch.manual_seed(3); a = sample(lg.clone(), top_k=8, top_p=0.8, temperature=0.9)
+    torch.manual_seed(3); b = O.sample(lg.clone(), top_k=8, top_p=0.8, temperature=0.9)
+    assert torch.equal(a, b)
+    torch.manual_seed(4); a = sample(lg.clone(), top_k=0, top_p=0.5, temperature=1.3)
+    torch.manual_seed(4); b = O.sample(lg.clone(), top_k=0, top_p=0.5, temperature=1.3)
+    assert torch.equal(a, b)
+
+
+def test_configs_match_reference_values():
+    assert MODEL_NAMES == ["evo-1.5-8k-base", "evo-1-8k-base", "evo-1-131k-base", "evo-1-8k-crispr", "evo-1-8k-transposon"]
+    c = get_config("evo-1-8k-base")
+    assert (c["hidden_size"], c["num_layers"], c["num_attention_heads"], c["state_size"], c["vocab_size"]) == (4096, 32, 32, 8, 512)
+    assert c["attn_layer_idxs"] == [8, 16, 24] and len(c["hyena_layer_idxs"]) == 29
+    assert c["eps"] == 1e-6 and c["short_filter_length"] == 3 and c["inner_size_multiple_of"] == 16
+    assert "rotary_emb_scaling_factor" not in c
+    c2 = get_config("evo-1-131k-base")
+    assert c2["use_interpolated_rotary_pos_emb"] is True and c2["rotary_emb_scaling_factor"] == 16
+    with pytest.raises(ValueError):
+        get_config("evo-2")
+    with pytest.raises(ValueError):
+        evo_b200.Evo("not-a-model")
+
+
+def test_dotdict():
+    d = dotdict({"a": 1}, Loader="x")
+    assert d.a == 1 and d.Loader == "x" and d.missing is None
+    d.b = 2
+    assert d["b"] == 2
+
+
+def test_parameter_tree_matches_checkpoint_keys_and_strict_loading():
+    cfg = O.tiny_config(num_layers=3, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    m = StripedHyena(dotdict(cfg))
+    spec = O.state_dict_spec(cfg)
+    sd = m.state_dict()
+    assert set(sd) == set(spec)
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    good = O.random_state_dict(cfg)
+    m.load_state_dict(good, strict=True)
+    bad = dict(good); bad.pop("blocks.0.filter.poles")
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    m.to_bfloat16_except_poles_residues()
+    for k, p in m.named_parameters():
+        assert p.dtype == (torch.float32 if ("poles" in k or "residues" in k) else torch.bfloat16), k
+    assert m.unembed is m.embedding_layer              # tied (evo/models.py:136-137)
+    ip = m.initialize_inference_params()
+    assert ip["mha"].max_seqlen == 8192 and ip["mha"].seqlen_offset == 0 and ip["hyena"].state_dim == 8
+    assert ip["hyena"].fir_state_dict == {} and ip["mha"].key_value_memory_dict == {}
+
+
+def test_no_cpu_path():
+    cfg = O.tiny_config(num_layers=1, attn_layer_idxs=(), hidden_size=256, num_heads=2)
+    m = StripedHyena(dotdict(cfg)).to_bfloat16_except_poles_residues()
+    with pytest.raises(evo_b200._lib.EvoError, match="CUDA"):
+        m(torch.zeros(1, 4, dtype=torch.long))
+
+
+class _OracleAsModel:
+    """CPU stand-in with the boundary protocol, to drive the host generation loop."""
+
+    def __init__(self, cfg, sd):
+        self.m = O.OracleStripedHyena(cfg, sd, torch.float32)
+        self.calls = []
+
+    def eval(self):
+        return self
+
+    def initialize_inference_params(self):
+        d = self.m.initialize_inference_params()
+        d["mha"].max_seqlen = 256
+        return d
+
+    def __call__(self, x, inference_params_dict=None):
+        self.calls.append((tuple(x.shape), None if inference_params_dict is None else inference_params_dict["mha"].seqlen_offset))
+        return self.m(x, inference_params_dict)
+
+
+@pytest.mark.parametrize("cached", [True, False])
+def test_generation_loop_protocol_and_greedy_parity(cached):
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=2)
+    model = _OracleAsModel(cfg, sd)
+    tok = CharLevelTokenizer(512)
+    g = Generator(model, tok, top_k=1)
+    prompt = torch.tensor([[65, 67, 71, 84, 65, 65]])
+    out_ids, out_logits, d = g.generate(device="cpu", input_ids=prompt, num_tokens=5, cached_generation=cached,
+                                        force_prompt_threshold=128, print_generation=False, stop_at_eos=False)
+    assert out_ids.shape == (1, 5) and out_logits.shape == (1, 5, 512)
+    # greedy continuation must equal repeated full forwards of the oracle
+    seq = prompt.clone()
+    for t in range(5):
+        lg, _ = model.m(seq)
+        nxt = lg[:, -1].argmax(-1)
+        assert nxt.item() == out_ids[0, t].item()
+        seq = torch.cat([seq, nxt[:, None]], 1)
+    if cached:
+        assert model.calls[0] == ((1, 6), 0)
+        assert model.calls[1] == ((1, 1), 6) and model.calls[2] == ((1, 1), 7)
+        assert set(d["hyena"].fir_state_dict) == {0} and set(d["mha"].key_value_memory_dict) == {1}
+    else:
+        assert d is None and model.calls[1][0] == (1, 7)
+
+
+def test_generation_prompt_forcing_bookkeeping():
+    """threshold < prompt length: prefill `thr` tokens, teacher-force the rest one by one;
+    the reference then sets seqlen_offset to the FULL prompt length (quirk Q1)."""
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    model = _OracleAsModel(cfg, O.random_state_dict(cfg, seed=2))
+    g = Generator(model, CharLevelTokenizer(512), top_k=1)
+    prompt = torch.tensor([[65, 67, 71, 84, 65, 65, 67, 67]])
+    out_ids, _, d = g.generate(device="cpu", input_ids=prompt, num_tokens=3, cached_generation=True,
+                               force_prompt_threshold=3, print_generation=False, stop_at_eos=False)
+    assert out_ids.shape == (1, 3)
+    assert model.calls[0] == ((1, 3), 0)
+    assert model.calls[1] == ((1, 1), 8)          # jump to len(prompt), not 3
+    assert len(model.calls) == 5 + 3

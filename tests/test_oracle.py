@@ -1,0 +1,165 @@
+"""The oracle against (a) flash_attn's own torch code paths (committed fixtures, the pinned
+part), (b) independent time-domain definitions of the Hyena operator, (c) itself across its
+execution modes (parallel / prefill+step), (d) its regression fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stripedhyena_oracle as O
+
+
+@pytest.fixture(scope="module")
+def att(golden_dir):
+    return np.load(os.path.join(golden_dir, "attention_flash_attn.npz"))
+
+
+@pytest.mark.parametrize("name,scaling", [("s1", 1.0), ("s16", 16.0)])
+def test_rotary_tables_match_flash_attn(att, name, scaling):
+    L, d = att["qkv"].shape[1], att["qkv"].shape[-1]
+    cos, sin = O.rotary_tables(L, d, scaling_factor=scaling, dtype=torch.float32)
+    np.testing.assert_array_equal(cos.numpy(), att[f"cos_{name}"])
+    np.testing.assert_array_equal(sin.numpy(), att[f"sin_{name}"])
+
+
+@pytest.mark.parametrize("name", ["s1", "s16"])
+def test_rotary_and_attention_match_flash_attn(att, name):
+    qkv = torch.from_numpy(att["qkv"])
+    cos, sin = torch.from_numpy(att[f"cos_{name}"]), torch.from_numpy(att[f"sin_{name}"])
+    q = O.apply_rotary(qkv[:, :, 0], cos, sin)
+    k = O.apply_rotary(qkv[:, :, 1], cos, sin)
+    np.testing.assert_allclose(q.numpy(), att[f"q_{name}"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(k.numpy(), att[f"k_{name}"], rtol=0, atol=2e-6)
+    ctx = O.causal_attention(q, k, qkv[:, :, 2])
+    # SelfAttention masks with -10000 instead of -inf (mha.py:271): same to fp32 precision
+    np.testing.assert_allclose(ctx.numpy(), att[f"ctx_{name}"], rtol=0, atol=3e-6)
+
+
+def _filter_params(D=64, S=8, seed=0):
+    cfg = O.tiny_config(num_layers=1, attn_layer_idxs=(), hidden_size=D, num_heads=1)
+    sd = O.random_state_dict(cfg, seed=seed)
+    return cfg, sd
+
+
+@pytest.mark.parametrize("L", [1, 2, 17, 64, 257])
+def test_fft_conv_equals_modal_recurrence(L):
+    """engine.parallel_iir's FFT long conv == the recurrence that defines the filter."""
+    D = 128
+    cfg = O.tiny_config(num_layers=1, attn_layer_idxs=(), hidden_size=D, num_heads=1)
+    sd = O.random_state_dict(cfg, seed=3)
+    p, r = sd["blocks.0.filter.poles"].double(), sd["blocks.0.filter.residues"].double()
+    torch.manual_seed(L)
+    z_pre = torch.randn(2, 3 * D, L, dtype=torch.float64)
+    Dk = torch.randn(D, dtype=torch.float64)
+    h = O.hyena_filter(p, r, L)
+    y, state = O.iir_parallel(z_pre, h, Dk, p, 1, D, want_state=True)
+    x2, x1, v = O.column_split(z_pre, 1, D)
+    conv, st = O.long_conv_direct(x1 * v, p, r)
+    y_ref = ((conv + (x1 * v) * Dk[:, None]) * x2).permute(0, 2, 1)
+    assert (y - y_ref).abs().max() < 1e-9
+    assert (state - st).abs().max() < 1e-9     # prefill_via_modal_fft == recurrence state
+
+
+def test_filter_is_sum_of_pole_powers():
+    cfg, sd = _filter_params()
+    p, r = sd["blocks.0.filter.poles"].double(), sd["blocks.0.filter.residues"].double()
+    h = O.hyena_filter(p, r, 33)[0]
+    pc, rc = torch.view_as_complex(p)[..., 0], torch.view_as_complex(r)[..., 0]
+    for t in (0, 1, 5, 32):
+        assert (h[:, t] - (rc * pc ** t).real.sum(-1)).abs().max() < 1e-12
+
+
+def test_column_split_mapping():
+    """x2 <- z[(c//hd)*3hd + c%hd], x1 <- +hd, v <- +2hd."""
+    H, hd = 3, 4
+    z = torch.arange(3 * H * hd, dtype=torch.float32)[None, :, None].repeat(1, 1, 2)
+    x2, x1, v = O.column_split(z, H, hd)
+    for c in range(H * hd):
+        base = (c // hd) * 3 * hd + c % hd
+        assert x2[0, c, 0] == base and x1[0, c, 0] == base + hd and v[0, c, 0] == base + 2 * hd
+
+
+def test_fir_step_equals_parallel():
+    cfg, sd = _filter_params(D=32)
+    w, b = sd["blocks.0.filter.short_filter_weight"].double(), sd["blocks.0.filter.short_filter_bias"].double()
+    torch.manual_seed(0)
+    u = torch.randn(2, 9, 96, dtype=torch.float64)
+    z, fir_state = O.fir_parallel(u[:, :8], w, b)
+    y, fs2 = O.fir_step(u[:, 8], fir_state.clone(), w, b)
+    zfull, _ = O.fir_parallel(u, w, b)
+    assert (y - zfull[..., 8]).abs().max() < 1e-12
+    assert torch.equal(fs2, u.permute(0, 2, 1)[..., -2:])
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 2e-3)])
+def test_stateful_equals_stateless(dtype, tol):
+    cfg = O.tiny_config(num_layers=3, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=5)
+    m = O.OracleStripedHyena(cfg, sd, dtype)
+    torch.manual_seed(0)
+    ids = torch.randint(0, 256, (2, 29))
+    full, _ = m(ids)
+    d = m.initialize_inference_params()
+    d["mha"].max_batch_size, d["mha"].max_seqlen = 2, 64
+    pre, d = m(ids[:, :20], d)
+    assert (pre - full[:, :20]).abs().max() < tol
+    d["mha"].seqlen_offset = d["hyena"].seqlen_offset = 20
+    for t in range(20, 29):
+        lg, d = m(ids[:, t:t + 1], d)
+        assert (lg[:, 0] - full[:, t]).abs().max() < tol
+        d["mha"].seqlen_offset += 1
+        d["hyena"].seqlen_offset += 1
+
+
+def test_strict_state_dict():
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg)
+    sd.pop("blocks.0.filter.D")
+    with pytest.raises(RuntimeError):
+        O.OracleStripedHyena(cfg, sd)
+
+
+def test_evo_7b_shapes():
+    cfg = O.evo_config("evo-1-131k-base")
+    spec = O.state_dict_spec(cfg)
+    assert O.mlp_inner_size(cfg) == 10928
+    assert spec["blocks.0.filter.poles"] == (4096, 8, 1, 2)
+    assert spec["blocks.8.inner_mha_cls.Wqkv.weight"] == (12288, 4096)
+    n = sum(int(np.prod(s)) for k, s in spec.items() if k != "unembed.weight" and "inv_freq" not in k)
+    assert abs(n - 6.45e9) < 0.03e9       # "7B" = 6.45 B parameters
+    assert cfg["rotary_emb_scaling_factor"] == 16
+
+
+def test_bf16_mode_close_to_truth():
+    cfg = O.tiny_config(num_layers=3, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=11)
+    ids = torch.randint(0, 4, (1, 64))
+    a, _ = O.OracleStripedHyena(cfg, sd, torch.bfloat16)(ids)
+    b, _ = O.OracleStripedHyena(cfg, sd, torch.float64)(ids)
+    la, lb = torch.log_softmax(a.double(), -1), torch.log_softmax(b, -1)
+    assert (la - lb).abs().mean() < 6e-2   # bf16 logits of magnitude ~10 carry ~2e-2 of rounding alone
+
+
+def test_regression_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny_model_oracle.npz"))
+    cfg = O.tiny_config(num_layers=3, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=7)
+    m = O.OracleStripedHyena(cfg, sd, torch.float64)
+    ids = torch.from_numpy(g["ids"])
+    logits, _ = m(ids)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], atol=2e-5, rtol=0)
+    d = m.initialize_inference_params()
+    d["mha"].max_batch_size, d["mha"].max_seqlen = 2, 128
+    m(ids[:, :40], d)
+    np.testing.assert_allclose(d["hyena"].state_dict[0].real.numpy(), g["state0_re"], atol=1e-5)
+    np.testing.assert_allclose(d["hyena"].fir_state_dict[0].float().numpy(), g["fir0"], atol=1e-6)
+
+
+def test_sample_greedy_and_topk():
+    torch.manual_seed(0)
+    lg = torch.randn(5, 512)
+    assert torch.equal(O.sample(lg, top_k=1), lg.argmax(-1))
+    s = O.sample(lg.clone(), top_k=4, top_p=0.9, temperature=0.7)
+    top4 = lg.topk(4, dim=-1).indices
+    assert all(s[i] in top4[i] for i in range(5))
