@@ -49,8 +49,10 @@ def load_checkpoint(model_name: str = "evo-1-8k-base", config_path: Optional[str
     cfg = dotdict(cfg)
 
     if random_init:
+        # build straight on the target device: no 26 GB fp32 host copy of a 7B model
         torch.manual_seed(seed)
-        model = StripedHyena(cfg)
+        with torch.device(device if device is not None else "cpu"):
+            model = StripedHyena(cfg)
     else:
         if model_dir is None:
             from huggingface_hub import snapshot_download

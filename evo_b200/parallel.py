@@ -1,0 +1,107 @@
+"""Sequence-parallel StripedHyena forward for contexts that do not fit / are too slow on one
+GPU (BASELINE.json configs[2]: evo-1-131k-base, batch 1 x 131072 nt over 8 B200).
+
+The reference has no multi-GPU code at all; this is new.  One process per
+GPU, weights replicated, every rank holds a contiguous slice of the sequence.  Token-local
+work (embedding, RMSNorm, every GEMM, the gated MLP, unembed) needs no communication.
+
+  Hyena layer      halo: the two z rows preceding the shard (all-gather of 2 rows per rank);
+                   carry: each rank scans its shard from a zero state and emits the end state
+                   (B, D, 8) complex64 -> ONE all-gather of 256 KB*B per rank -> every rank folds
+                   S_in = sum_{q<r} p^{(r-1-q) Lr} E_q (evo_hyena_combine_states) and runs the
+                   output scan from S_in.  Exact: it is the modal recurrence itself.
+  Attention layer  K and V of earlier shards are all-gathered (bf16, 2*Lr*D per rank); rank r
+                   attends its Lr queries over keys [0, (r+1) Lr).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_BIAS_RESID, EPI_NONE, EPI_RESID, AttnParams, HyenaParams, check, ptr
+
+
+def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: int, group=None):
+    """ids_local: (B, L/world) slice `rank` of the token ids.  Returns the logits of the slice,
+    (B, L/world, V) bf16.  Stateless (scoring) forward only."""
+    model._ensure_packed()
+    cfg = model.config
+    lib = _lib.lib()
+    dev = ids_local.device
+    B, Lr = ids_local.shape
+    M = B * Lr
+    d, H, V = cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size
+    hd = d // H
+    S = cfg.state_size
+    stream = model._stream
+    with torch.cuda.device(dev), torch.no_grad():
+        ids_local = ids_local.contiguous()
+        u = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
+        check(lib.evo_embed(ptr(ids_local), int(ids_local.dtype == torch.int64), ptr(model.embedding_layer.weight), ptr(u), M, d, V, stream()), "evo_embed")
+        for i, blk in enumerate(model.blocks):
+            xn = torch.empty_like(u)
+            model._rmsnorm(u, blk.pre_norm.scale, xn, M)
+            if i in model._attn_idxs:
+                mha = blk.inner_mha_cls
+                qkv = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
+                model._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
+                pos0 = rank * Lr
+                cos, sin = model._rope_tables(pos0 + Lr, dev)
+                check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + pos0 * (hd // 2) * 2), C.c_void_p(sin.data_ptr() + pos0 * (hd // 2) * 2),
+                                        B, Lr, H, hd, stream()), "evo_rotary_qk")
+                kv_local = qkv.view(B, Lr, 3, d)[:, :, 1:].contiguous()                    # (B, Lr, 2, D)
+                kv_all = _all_gather(kv_local, world, group)                               # (W, B, Lr, 2, D)
+                Lk = (rank + 1) * Lr
+                kv = kv_all[: rank + 1].permute(1, 0, 2, 3, 4).reshape(B, Lk, 2 * d)
+                kv = kv if kv.is_contiguous() else kv.contiguous()
+                ctx = xn
+                ap = AttnParams(out=ctx.data_ptr(), B=B, Lq=Lr, Lk=Lk, H=H, hd=hd, q_pos0=pos0, softmax_scale=1.0 / math.sqrt(hd))
+                ap.q, ap.q_tok_stride, ap.q_batch_stride = qkv.data_ptr(), 3 * d, Lr * 3 * d
+                ap.k, ap.v, ap.kv_tok_stride, ap.kv_batch_stride = kv.data_ptr(), kv.data_ptr() + d * 2, 2 * d, Lk * 2 * d
+                n = lib.evo_attn_fwd_workspace(C.byref(ap), model.attn_variant)
+                ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+                check(lib.evo_attn_fwd_ws(C.byref(ap), model.attn_variant, ptr(ws), n, stream()), "evo_attn_fwd")
+                u2 = torch.empty_like(u)
+                model._gemm(ctx, mha.out_proj.weight, u2, M, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID, bias=mha.out_proj.bias, resid=u)
+            else:
+                f = blk.filter
+                z = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
+                model._gemm(xn, blk.projections.weight, z, M, 3 * d, d, EPI_BIAS, bias=blk.projections.bias)
+                tails = _all_gather(z.view(B, Lr, 3 * d)[:, -2:], world, group)            # (W, B, 2, 3D)
+                halo = tails[rank - 1].contiguous() if rank > 0 else None
+                end = torch.empty(B, d, S, 2, dtype=torch.float32, device=dev)
+                hp = HyenaParams(z=z.data_ptr(), y=None, fir_w=f.short_filter_weight.data_ptr(), fir_b=f.short_filter_bias.data_ptr(), Dskip=f.D.data_ptr(),
+                                 poles=f.poles.data_ptr(), residues=f.residues.data_ptr(), B=B, L=Lr, D=d, S=S, nheads=H,
+                                 halo=halo.data_ptr() if halo is not None else None, state_in=None, state_out=end.data_ptr(), fir_state_out=None,
+                                 force_segments=0, state_only=1)
+                n = lib.evo_hyena_fwd_workspace(C.byref(hp))
+                ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+                check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), n, stream()), "evo_hyena_fwd(state)")
+                ends = _all_gather(end, world, group)                                      # (W, B, D, S, 2)
+                s_in = torch.empty_like(end)
+                check(lib.evo_hyena_combine_states(ptr(ends), ptr(s_in), ptr(f.poles), rank, world, Lr, B, d, S, stream()), "evo_hyena_combine_states")
+                y = xn
+                hp.y, hp.state_in, hp.state_out, hp.state_only = y.data_ptr(), s_in.data_ptr(), None, 0
+                n2 = lib.evo_hyena_fwd_workspace(C.byref(hp))
+                ws2 = torch.empty(max(n2, 1), dtype=torch.uint8, device=dev)
+                check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws2), n2, stream()), "evo_hyena_fwd")
+                u2 = torch.empty_like(u)
+                model._gemm(y, blk.out_filter_dense.weight, u2, M, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u)
+            u = model._mlp_residual(i, blk, u2, M)
+        if model.norm is not None:
+            xn = torch.empty_like(u)
+            model._rmsnorm(u, model.norm.scale, xn, M)
+            u = xn
+        logits = torch.empty(M, V, dtype=torch.bfloat16, device=dev)
+        model._gemm(u, model.unembed.weight, logits, M, V, d, EPI_NONE)
+    return logits.view(B, Lr, V)

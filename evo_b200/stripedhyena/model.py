@@ -28,8 +28,8 @@ from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID
 from .cache import InferenceParams, RecurrentInferenceParams
 
 # kernel variants (see include/evo_b200.h); overridable for experiments
-GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "0"))
-ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "0"))
+GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "1"))
+ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "1"))
 
 
 def _round_up(x: int, m: int) -> int:
@@ -143,6 +143,7 @@ class StripedHyena(nn.Module):
         self._rope = None
         self.gemm_variant = GEMM_VARIANT
         self.attn_variant = ATTN_VARIANT
+        self._prof = None   # set to a list to record (kind, algorithmic work, start event, end event) per kernel call
 
     # ---- reference API ------------------------------------------------------------------
     def to_bfloat16_except_poles_residues(self):
@@ -206,12 +207,22 @@ class StripedHyena(nn.Module):
     def _stream():
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def _record(self, kind, work, launch):
+        """Run `launch()`; when profiling is on, bracket it with CUDA events on the launch stream."""
+        if self._prof is None:
+            return launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        self._prof.append((kind, work, e0, e1))
+
     def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None):
         p = GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=ldc or N,
                        bias=bias.data_ptr() if bias is not None else None,
                        residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
                        M=M, N=N, K=K, epilogue=epi, variant=self.gemm_variant)
-        check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm")
+        self._record("gemm", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
 
     def _rmsnorm(self, x, scale, out, rows):
         check(_lib.lib().evo_rmsnorm(ptr(x), ptr(scale), ptr(out), rows, self.config.hidden_size,
@@ -279,7 +290,7 @@ class StripedHyena(nn.Module):
                 hp.state_out, hp.fir_state_out = st_out.data_ptr(), fs_out.data_ptr()
             ws_bytes = lib.evo_hyena_fwd_workspace(C.byref(hp))
             ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-            check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), ws_bytes, self._stream()), "evo_hyena_fwd")
+            self._record("hyena", 8.0 * B * L * d, lambda: check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), ws_bytes, self._stream()), "evo_hyena_fwd"))
             if ip is not None:
                 ip.state_dict[i] = torch.view_as_complex(st_out)
                 ip.fir_state_dict[i] = fs_out
@@ -321,7 +332,8 @@ class StripedHyena(nn.Module):
             ap.kv_tok_stride, ap.kv_batch_stride, ap.Lk = 2 * d, cache.shape[1] * 2 * d, off + L
         ws_bytes = lib.evo_attn_fwd_workspace(C.byref(ap), self.attn_variant)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-        check(lib.evo_attn_fwd_ws(C.byref(ap), self.attn_variant, ptr(ws), ws_bytes, self._stream()), "evo_attn_fwd")
+        causal_flops = 4.0 * B * H * hd * (L * (off + (L + 1) / 2.0))   # QK^T + PV over the visible (query, key) pairs
+        self._record("attn", causal_flops, lambda: check(lib.evo_attn_fwd_ws(C.byref(ap), self.attn_variant, ptr(ws), ws_bytes, self._stream()), "evo_attn_fwd"))
         u2 = torch.empty_like(u)
         self._gemm(ctx, mha.out_proj.weight, u2, M, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID,
                    bias=mha.out_proj.bias, resid=u)
