@@ -32,7 +32,8 @@ def _digest(paths):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "evo_b200.h")]
+    hdrs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(HERE, "..", "include", "evo_b200.h"))
     stamp = os.path.join(OBJ, "stamp")
     dig = _digest(srcs + hdrs)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:

@@ -173,13 +173,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
       float s[BKV];
-#pragma unroll
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t t[32];
-        tmem_ld_32x32(lane_addr + TM_S0 + sb * BKV + c, t);
+      {   // all four 32-column loads in flight, one wait
+        uint32_t t0[32], t1[32], t2[32], t3[32];
+        const uint32_t sa = lane_addr + TM_S0 + sb * BKV;
+        tmem_ld_32x32(sa, t0); tmem_ld_32x32(sa + 32, t1); tmem_ld_32x32(sa + 64, t2); tmem_ld_32x32(sa + 96, t3);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c + i] = __uint_as_float(t[i]);
+        for (int i = 0; i < 32; ++i) {
+          s[i] = __uint_as_float(t0[i]); s[32 + i] = __uint_as_float(t1[i]);
+          s[64 + i] = __uint_as_float(t2[i]); s[96 + i] = __uint_as_float(t3[i]);
+        }
       }
       tc_fence_before();
       mbar_arrive(&s_empty[sb]);
@@ -189,9 +192,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < BKV; ++i) if (key0 + i > pos) s[i] = -INFINITY;
       }
-      float mx = s[0];
+      // row max: 8 independent chains (a single warp per SMSP cannot hide a 128-long dependent chain)
+      float mxs[8];
 #pragma unroll
-      for (int i = 1; i < BKV; ++i) mx = fmaxf(mx, s[i]);
+      for (int q8 = 0; q8 < 8; ++q8) mxs[q8] = s[q8];
+#pragma unroll
+      for (int i = 8; i < BKV; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], s[i]);
+      float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])), fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       mx *= a.scale_log2;
       // lazy rescale: keep the old reference unless the max grew by more than 2^8
       float alpha = 1.f;
@@ -200,7 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       else if (grow) { alpha = ex2(m_ref - mx); m_ref = mx; l *= alpha; }
       // P = exp2(s*scale - m_ref), written as bf16 into the swizzled A-operand tile
       uint8_t* prow = sP + sb * TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-      float lsum = 0.f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 16; ++c) {                          // 16-byte chunks: 8 keys each
         uint32_t w[4];
@@ -208,12 +215,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int i = 0; i < 4; ++i) {
           float p0 = ex2(fmaf(s[c * 8 + 2 * i], a.scale_log2, -m_ref));
           float p1 = ex2(fmaf(s[c * 8 + 2 * i + 1], a.scale_log2, -m_ref));
-          lsum += p0 + p1;
+          ls[i] += p0 + p1;
           w[i] = pack_bf16(p0, p1);
         }
         uint8_t* dst = prow + (c >> 3) * HALF_BYTES + (((c & 7) ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       l += lsum;
       // O rescale (warp-collective because tcgen05.ld/st are): needs PV(j-1) finished
       if (j > 0) {

@@ -125,7 +125,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C_::STAGES; ++i) { mbar_init(&full[i], CG); mbar_init(&empty[i], 1); }
+    // full: one arrival (the leader's arrive.expect_tx); the byte count covers both CTAs' loads
+    for (int i = 0; i < C_::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
     fence_barrier_init();
   }
@@ -156,8 +157,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(smA + stage * C_::A_BYTES, &tmA, &full[stage], kb * BK, a_row);
             tma_load_2d(smB + stage * C_::B_BYTES, &tmB, &full[stage], kb * BK, b_row);
           } else {
+            // no remote arrive from the peer: a release.cluster arrive per stage costs more than the
+            // 512-cycle k-block budget; the peer's bytes are already counted in the leader's expect_tx
             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C_::STAGE_BYTES);
-            else        mbar_arrive_cluster(&full[stage], 0);
             const uint32_t bar = smem_u32(&full[stage]) & full_leader_mask;
             tma_load_2d_2sm(smA + stage * C_::A_BYTES, &tmA, bar, kb * BK, a_row);
             tma_load_2d_2sm(smB + stage * C_::B_BYTES, &tmB, bar, kb * BK, b_row);
@@ -221,7 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if constexpr (CG == 1) mbar_arrive(&tempty[acc]); else mbar_arrive_cluster(&tempty[acc], 0); }
+      if (lane == 0) { if constexpr (CG == 1) mbar_arrive(&tempty[acc]); else mbar_arrive_cluster_relaxed(&tempty[acc], 0); }
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   }

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "../../include/evo_b200.h"
 #include <algorithm>
+#include "hyena_tma.cuh"
 
 using namespace evo;
 
@@ -266,13 +267,20 @@ __global__ void hyena_step_kernel(const bf16* __restrict__ u, bf16* __restrict__
   y[idx] = __float2bfloat16_rn(x2 * (acc + dv));
 }
 
+bool use_tma_path(const evo_hyena_params* p) {
+  return p->D % evo_hy2::CH_PER_CTA == 0 && p->D / p->nheads == 128;
+}
+
+// Sequential-in-L is the efficient form (one HBM pass, no carry pass); split L only when the
+// (channel block x batch) grid cannot occupy the chip.
 int pick_segments(const evo_hyena_params* p) {
   const long long L = p->L;
   if (p->force_segments > 0) return (int)std::min<long long>(p->force_segments, std::max<long long>(1, L));
-  long long blocks = (long long)((p->D + THREADS - 1) / THREADS) * p->B;
+  const int per_cta = use_tma_path(p) ? evo_hy2::CH_PER_CTA : THREADS;
+  long long blocks = (long long)((p->D + per_cta - 1) / per_cta) * p->B;
   int sms = device_sm_count();
-  if (blocks >= sms || L < 1024) return 1;
-  long long want = (2LL * sms + blocks - 1) / blocks;
+  if (blocks * 5 >= sms * 3 || L < 1024) return 1;
+  long long want = (sms + blocks - 1) / blocks;
   long long max_by_len = std::max<long long>(1, L / 512);
   return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(want, max_by_len), 64));
 }
@@ -280,9 +288,17 @@ int pick_segments(const evo_hyena_params* p) {
 }  // namespace
 
 extern "C" size_t evo_hyena_fwd_workspace(const evo_hyena_params* p) {
+  if (p->L <= 0) return 0;
   int nseg = pick_segments(p);
   if (nseg <= 1 && !p->state_only) return 0;
   return (size_t)p->B * nseg * p->D * NS * 2 * sizeof(float);
+}
+
+// segment geometry: equal segments, none empty
+static void segment_geometry(const evo_hyena_params* p, int& nseg, long long& seg_len) {
+  nseg = pick_segments(p);
+  seg_len = (p->L + nseg - 1) / nseg;
+  nseg = (int)((p->L + seg_len - 1) / seg_len);
 }
 
 extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t workspace_bytes, void* stream) {
@@ -291,36 +307,71 @@ extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t 
   EVO_REQUIRE(p->B > 0 && p->B <= 65535, "evo_hyena_fwd: bad batch %d", p->B);
   if (p->L == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int nseg = pick_segments(p);
+  int nseg; long long seg_len;
+  segment_geometry(p, nseg, seg_len);
   size_t need = evo_hyena_fwd_workspace(p);
   EVO_REQUIRE(workspace_bytes >= need && (need == 0 || workspace), "evo_hyena_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
-  Args a;
-  a.z = (const bf16*)p->z; a.y = (bf16*)p->y;
-  a.fir_w = (const bf16*)p->fir_w; a.fir_b = (const bf16*)p->fir_b; a.Dskip = (const bf16*)p->Dskip;
-  a.poles = p->poles; a.residues = p->residues;
-  a.halo = (const bf16*)p->halo; a.state_in = p->state_in; a.state_out = p->state_out;
-  a.seg_states = (float*)workspace;
-  a.B = p->B; a.D = p->D; a.hd = p->D / p->nheads; a.nseg = nseg; a.L = p->L;
-  a.seg_len = (p->L + nseg - 1) / nseg;
-  dim3 block(THREADS);
-  dim3 grid((p->D + THREADS - 1) / THREADS, p->B, nseg);
+  if (p->state_only) EVO_REQUIRE(p->state_out != nullptr, "evo_hyena_fwd: state_only needs state_out");
+  else EVO_REQUIRE(p->y != nullptr, "evo_hyena_fwd: y is NULL");
   int rc;
-  if (p->state_only) {
-    EVO_REQUIRE(p->state_out != nullptr, "evo_hyena_fwd: state_only needs state_out");
-    hyena_scan_kernel<true><<<grid, block, 0, st>>>(a);
-    if ((rc = check_launch("hyena_scan<state>"))) return rc;
-    int n = p->B * p->D * NS;
-    hyena_fold_states_kernel<<<(n + 255) / 256, 256, 0, st>>>(a.seg_states, p->state_in, p->poles, p->state_out, p->B, p->D, nseg, a.seg_len, p->L);
-    if ((rc = check_launch("hyena_fold_states"))) return rc;
-  } else {
-    EVO_REQUIRE(p->y != nullptr, "evo_hyena_fwd: y is NULL");
-    if (nseg > 1) {
-      dim3 g2(grid.x, grid.y, nseg - 1);     // the last segment's zero-start state is never needed
-      hyena_scan_kernel<true><<<g2, block, 0, st>>>(a);
-      if ((rc = check_launch("hyena_scan<state>"))) return rc;
+  if (use_tma_path(p)) {
+    using namespace evo_hy2;
+    CUtensorMap tmZ;
+    uint64_t dims[3] = {(uint64_t)3 * p->D, (uint64_t)p->L, (uint64_t)p->B};
+    uint64_t str[2] = {(uint64_t)3 * p->D * 2, (uint64_t)p->L * 3 * p->D * 2};
+    uint32_t box[3] = {128, (uint32_t)T2, 1};
+    if ((rc = make_tmap_nd_bf16(&tmZ, p->z, 3, dims, str, box, false))) return rc;
+    Args2 a;
+    a.y = (bf16*)p->y; a.z = (const bf16*)p->z;
+    a.fir_w = (const bf16*)p->fir_w; a.fir_b = (const bf16*)p->fir_b; a.Dskip = (const bf16*)p->Dskip;
+    a.poles = p->poles; a.residues = p->residues; a.halo = (const bf16*)p->halo; a.state_in = p->state_in; a.state_out = p->state_out;
+    a.seg_states = (float*)workspace; a.B = p->B; a.D = p->D; a.nseg = nseg; a.L = p->L; a.seg_len = seg_len;
+    static bool attr_done = false;
+    if (!attr_done) {
+      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_done = true;
     }
-    hyena_scan_kernel<false><<<grid, block, 0, st>>>(a);
-    if ((rc = check_launch("hyena_scan<out>"))) return rc;
+    dim3 grid(p->D / CH_PER_CTA, p->B, nseg), block(evo_hy2::THREADS);
+    if (p->state_only) {
+      hyena_scan_tma_kernel<true><<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
+      if ((rc = check_launch("hyena_scan_tma<state>"))) return rc;
+    } else {
+      if (nseg > 1) {
+        dim3 g2(grid.x, grid.y, nseg - 1);
+        hyena_scan_tma_kernel<true><<<g2, block, SMEM_BYTES, st>>>(tmZ, a);
+        if ((rc = check_launch("hyena_scan_tma<state>"))) return rc;
+      }
+      hyena_scan_tma_kernel<false><<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
+      if ((rc = check_launch("hyena_scan_tma<out>"))) return rc;
+    }
+  } else {
+    Args a;
+    a.z = (const bf16*)p->z; a.y = (bf16*)p->y;
+    a.fir_w = (const bf16*)p->fir_w; a.fir_b = (const bf16*)p->fir_b; a.Dskip = (const bf16*)p->Dskip;
+    a.poles = p->poles; a.residues = p->residues;
+    a.halo = (const bf16*)p->halo; a.state_in = p->state_in; a.state_out = p->state_out;
+    a.seg_states = (float*)workspace;
+    a.B = p->B; a.D = p->D; a.hd = p->D / p->nheads; a.nseg = nseg; a.L = p->L; a.seg_len = seg_len;
+    dim3 block(THREADS);
+    dim3 grid((p->D + THREADS - 1) / THREADS, p->B, nseg);
+    if (p->state_only) {
+      hyena_scan_kernel<true><<<grid, block, 0, st>>>(a);
+      if ((rc = check_launch("hyena_scan<state>"))) return rc;
+    } else {
+      if (nseg > 1) {
+        dim3 g2(grid.x, grid.y, nseg - 1);     // the last segment's zero-start state is never needed
+        hyena_scan_kernel<true><<<g2, block, 0, st>>>(a);
+        if ((rc = check_launch("hyena_scan<state>"))) return rc;
+      }
+      hyena_scan_kernel<false><<<grid, block, 0, st>>>(a);
+      if ((rc = check_launch("hyena_scan<out>"))) return rc;
+    }
+  }
+  if (p->state_only) {
+    int n = p->B * p->D * NS;
+    hyena_fold_states_kernel<<<(n + 255) / 256, 256, 0, st>>>((const float*)workspace, p->state_in, p->poles, p->state_out, p->B, p->D, nseg, seg_len, p->L);
+    if ((rc = check_launch("hyena_fold_states"))) return rc;
   }
   if (p->fir_state_out) {
     long long n = (long long)p->B * 3 * p->D;

@@ -1,0 +1,229 @@
+// Hyena scan, TMA-staged variant (the production path for head_dim 128 / D % 256 == 0).
+//
+// Same operator and rounding points as hyena_scan_kernel (hyena.cu); what changes is how the
+// machine is driven:
+//   * a CTA owns two heads (256 channels) of one batch row and walks its L segment in tiles of
+//     T2 tokens; warp 4 is a TMA producer that keeps a 4-deep mbarrier ring of z tiles
+//     ([x2|x1|v] x 2 heads = six 128-column boxes, 24 KB per stage) in flight, so HBM latency is
+//     never exposed to the scan;
+//   * each of the 128 compute threads carries TWO adjacent channels and does all fp32 work with
+//     packed fma.rn.f32x2 (FFMA2): Blackwell's FP32 pipe only reaches its 128 lanes/SM/clk
+//     through the packed form, and it halves the instruction count of the 8-state recurrence;
+//   * x2/x1/v are read from smem as bf16x2 words (conflict-free: lane l reads word l), y is
+//     written as bf16x2 words, 128 B per warp per token.
+#pragma once
+#include "common.cuh"
+
+namespace evo_hy2 {
+
+using namespace evo;
+
+constexpr int NS = 8;
+constexpr int T2 = 16;                       // tokens per stage
+constexpr int STAGES = 4;
+constexpr int CH_PER_CTA = 256;              // two heads of 128
+constexpr int SUB_BYTES = T2 * 128 * 2;      // one 128-column box
+constexpr int STAGE_BYTES = 6 * SUB_BYTES;   // [head0: x2 x1 v][head1: x2 x1 v]
+constexpr int THREADS = 160;                 // 4 compute warps + 1 producer warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + 1024;
+
+struct Args2 {
+  bf16* y;
+  const bf16* z;
+  const bf16* fir_w; const bf16* fir_b; const bf16* Dskip;
+  const float* poles; const float* residues;
+  const bf16* halo; const float* state_in;
+  float* state_out;
+  float* seg_states;
+  int B, D, nseg;
+  long long L, seg_len;
+};
+
+__device__ __forceinline__ float2 unpack2(uint32_t v) { return make_float2(bf_lo(v), bf_hi(v)); }
+__device__ __forceinline__ float2 rbf2(float2 a) { return unpack2(pack_bf16(a.x, a.y)); }
+__device__ __forceinline__ float2 ld_bf2(const bf16* p) { return unpack2(__ldg(reinterpret_cast<const unsigned int*>(p))); }
+
+struct C2 { float2 r, i; };                  // two complex numbers (one per channel of the pair)
+__device__ __forceinline__ C2 cmul2(C2 a, C2 b) {
+  C2 o;
+  o.r = __ffma2_rn(a.r, b.r, __fmul2_rn(make_float2(-a.i.x, -a.i.y), b.i));
+  o.i = __ffma2_rn(a.r, b.i, __fmul2_rn(a.i, b.r));
+  return o;
+}
+__device__ __forceinline__ C2 cpow2(C2 p, long long n) {
+  C2 acc; acc.r = make_float2(1.f, 1.f); acc.i = make_float2(0.f, 0.f);
+  while (n > 0) { if (n & 1) acc = cmul2(acc, p); p = cmul2(p, p); n >>= 1; }
+  return acc;
+}
+
+template <bool STATE_ONLY>
+__global__ void __launch_bounds__(THREADS, 1)
+hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cb = blockIdx.x, b = blockIdx.y, seg = blockIdx.z;
+  const long long t0 = (long long)seg * a.seg_len;
+  const long long t1 = min(a.L, t0 + a.seg_len);
+  const int n_tiles = t1 > t0 ? (int)((t1 - t0 + T2 - 1) / T2) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmZ);
+      for (int k = 0; k < n_tiles; ++k) {
+        const int st = k % STAGES;
+        mbar_wait(&empty[st], ((uint32_t)(k / STAGES) & 1) ^ 1);
+        uint8_t* dst = smem + st * STAGE_BYTES;
+        const int row = (int)(t0 + (long long)k * T2);
+        if (STATE_ONLY) {
+          mbar_arrive_expect_tx(&full[st], 4 * SUB_BYTES);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int w = 1; w < 3; ++w)
+              tma_load_3d(dst + (hh * 3 + w) * SUB_BYTES, &tmZ, &full[st], cb * 768 + hh * 384 + w * 128, row, b);
+        } else {
+          mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+#pragma unroll
+          for (int s6 = 0; s6 < 6; ++s6)
+            tma_load_3d(dst + s6 * SUB_BYTES, &tmZ, &full[st], cb * 768 + s6 * 128, row, b);
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------ compute warps: thread = channel pair
+  const int hh = warp >> 1;                               // head within the CTA
+  const int j2 = ((warp & 1) * 32 + lane) * 2;            // first channel of the pair inside the head
+  const int ch = cb * CH_PER_CTA + hh * 128 + j2;         // global channel (of D)
+  const int zc = cb * 768 + hh * 384 + j2;                // z column of x2; x1 = +128, v = +256
+  const long long C3 = 3LL * a.D;
+
+  float2 pr[NS], pi[NS], npi[NS], rr[NS], ri[NS], sr[NS], si[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    float2 p0 = __ldg(reinterpret_cast<const float2*>(a.poles) + (long long)ch * NS + s);
+    float2 p1 = __ldg(reinterpret_cast<const float2*>(a.poles) + (long long)(ch + 1) * NS + s);
+    float2 r0 = __ldg(reinterpret_cast<const float2*>(a.residues) + (long long)ch * NS + s);
+    float2 r1 = __ldg(reinterpret_cast<const float2*>(a.residues) + (long long)(ch + 1) * NS + s);
+    pr[s] = make_float2(p0.x, p1.x); pi[s] = make_float2(p0.y, p1.y); npi[s] = make_float2(-p0.y, -p1.y);
+    rr[s] = make_float2(r0.x, r1.x); ri[s] = make_float2(-r0.y, -r1.y);
+    sr[s] = make_float2(0.f, 0.f); si[s] = make_float2(0.f, 0.f);
+  }
+  // FIR taps / bias / skip for the pair: w[k] = (tap k of channel c, tap k of channel c+1)
+  float2 w1[3], wv[3], w2[3], b1, bv, b2, dsk;
+  {
+    auto taps = [&](int c, float2 (&w)[3]) {
+      const bf16* p0 = a.fir_w + (long long)c * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w[k] = make_float2(__bfloat162float(p0[k]), __bfloat162float(p0[3 + k]));
+    };
+    taps(zc + 128, w1); taps(zc + 256, wv); taps(zc, w2);
+    b1 = ld_bf2(a.fir_b + zc + 128); bv = ld_bf2(a.fir_b + zc + 256); b2 = ld_bf2(a.fir_b + zc);
+    dsk = ld_bf2(a.Dskip + ch);
+  }
+
+  if (!STATE_ONLY) {
+    if (a.state_in) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        float2 v0 = __ldg(reinterpret_cast<const float2*>(a.state_in) + ((long long)b * a.D + ch) * NS + s);
+        float2 v1 = __ldg(reinterpret_cast<const float2*>(a.state_in) + ((long long)b * a.D + ch + 1) * NS + s);
+        sr[s] = make_float2(v0.x, v1.x); si[s] = make_float2(v0.y, v1.y);
+      }
+    }
+    if (seg > 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        C2 p; p.r = pr[s]; p.i = pi[s];
+        const C2 pl = cpow2(p, a.seg_len);
+        C2 acc; acc.r = sr[s]; acc.i = si[s];
+        for (int q = 0; q < seg; ++q) {
+          const float2* e = reinterpret_cast<const float2*>(a.seg_states) + (((long long)b * a.nseg + q) * a.D + ch) * NS + s;
+          float2 e0 = e[0], e1 = e[NS];
+          acc = cmul2(pl, acc);
+          acc.r = __fadd2_rn(acc.r, make_float2(e0.x, e1.x));
+          acc.i = __fadd2_rn(acc.i, make_float2(e0.y, e1.y));
+        }
+        sr[s] = acc.r; si[s] = acc.i;
+      }
+    }
+  }
+
+  // FIR history z[t0-2], z[t0-1]
+  const bf16* zb = a.z + (long long)b * a.L * C3;
+  float2 h1[2], hv[2], h2[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    h1[k] = hv[k] = h2[k] = make_float2(0.f, 0.f);
+    long long t = t0 - 2 + k;
+    const bf16* row = nullptr;
+    if (t >= 0) row = zb + t * C3;
+    else if (a.halo) row = a.halo + ((long long)b * 2 + (t + 2)) * C3;
+    if (row) { h1[k] = ld_bf2(row + zc + 128); hv[k] = ld_bf2(row + zc + 256); if (!STATE_ONLY) h2[k] = ld_bf2(row + zc); }
+  }
+
+  uint32_t* yrow = STATE_ONLY ? nullptr : reinterpret_cast<uint32_t*>(a.y + ((long long)b * a.L + t0) * a.D + ch);
+  const long long ystride = a.D / 2;        // in 32-bit words
+
+  for (int k = 0; k < n_tiles; ++k) {
+    const int st = k % STAGES;
+    mbar_wait(&full[st], (uint32_t)(k / STAGES) & 1);
+    const uint8_t* tile = smem + st * STAGE_BYTES + hh * 3 * SUB_BYTES + j2 * 2;
+    const int n_tok = (int)min((long long)T2, t1 - (t0 + (long long)k * T2));
+#pragma unroll 4
+    for (int j = 0; j < T2; ++j) {
+      if (j < n_tok) {
+        const float2 z1 = unpack2(*reinterpret_cast<const uint32_t*>(tile + 1 * SUB_BYTES + j * 256));
+        const float2 zv = unpack2(*reinterpret_cast<const uint32_t*>(tile + 2 * SUB_BYTES + j * 256));
+        // short FIR: conv (fp32 accumulate, rp) then bias (rp)
+        float2 f1 = rbf2(__fadd2_rn(rbf2(__ffma2_rn(w1[2], z1, __ffma2_rn(w1[1], h1[1], __fmul2_rn(w1[0], h1[0])))), b1));
+        float2 fv = rbf2(__fadd2_rn(rbf2(__ffma2_rn(wv[2], zv, __ffma2_rn(wv[1], hv[1], __fmul2_rn(wv[0], hv[0])))), bv));
+        h1[0] = h1[1]; h1[1] = z1; hv[0] = hv[1]; hv[1] = zv;
+        const float2 x = rbf2(__fmul2_rn(f1, fv));               // x1v (rp)
+        float2 accr = make_float2(0.f, 0.f), acci = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const float2 t_ = __ffma2_rn(npi[s], si[s], x);
+          const float2 nr = __ffma2_rn(pr[s], sr[s], t_);
+          const float2 ni = __ffma2_rn(pr[s], si[s], __fmul2_rn(pi[s], sr[s]));
+          sr[s] = nr; si[s] = ni;
+          if (!STATE_ONLY) { accr = __ffma2_rn(rr[s], nr, accr); acci = __ffma2_rn(ri[s], ni, acci); }
+        }
+        if (!STATE_ONLY) {
+          const float2 z2 = unpack2(*reinterpret_cast<const uint32_t*>(tile + j * 256));
+          const float2 f2 = rbf2(__fadd2_rn(rbf2(__ffma2_rn(w2[2], z2, __ffma2_rn(w2[1], h2[1], __fmul2_rn(w2[0], h2[0])))), b2));
+          h2[0] = h2[1]; h2[1] = z2;
+          const float2 yc = rbf2(__fadd2_rn(accr, acci));         // y.to(bf16) (rp)
+          const float2 u = rbf2(__fadd2_rn(yc, rbf2(__fmul2_rn(x, dsk))));   // y + x1v*D (rp, rp)
+          const float2 o = __fmul2_rn(u, f2);                     // * x2 (rp on pack)
+          yrow[((long long)k * T2 + j) * ystride] = pack_bf16(o.x, o.y);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+
+  float* dst = nullptr;
+  if (STATE_ONLY) dst = a.seg_states + ((((long long)b * a.nseg + seg) * a.D + ch) * NS) * 2;
+  else if (a.state_out && seg == a.nseg - 1) dst = a.state_out + (((long long)b * a.D + ch) * NS) * 2;
+  if (dst && n_tiles >= 0) {
+    float2* e = reinterpret_cast<float2*>(dst);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { e[s] = make_float2(sr[s].x, si[s].x); e[NS + s] = make_float2(sr[s].y, si[s].y); }
+  }
+}
+
+}  // namespace evo_hy2

@@ -522,3 +522,29 @@ def _top_p_filter(logits, top_p):
     cp = sl.softmax(dim=-1).cumsum(dim=-1)
     rem = cp <= (1 - top_p)
     logits.masked_fill_(rem.scatter(1, si, rem), float("-inf"))
+
+
+# --------------------------------------------------------------------------
+# Time-domain form of the Hyena operator with explicit history (tests: continued prefill,
+# sequence sharding).  Wide arithmetic only; the algebra, not the rounding, is what it checks.
+# --------------------------------------------------------------------------
+
+def hyena_operator_time_domain(z, fir_w, fir_b, Dskip, poles, residues, num_heads, head_dim, halo=None, state_in=None):
+    """z (B, L, 3D) float64.  halo (B, 2, 3D): the two z rows before row 0 (zeros if None);
+    state_in (B, D, S) complex128: modal state before row 0.  Returns y (B, L, D) float64 and
+    the state after the last row."""
+    B, L, C3 = z.shape
+    zz = torch.cat([halo if halo is not None else torch.zeros(B, 2, C3, dtype=z.dtype), z], dim=1)
+    w = fir_w.to(z.dtype)[:, 0]                                                     # (3D, 3)
+    zp = zz[:, 0:L] * w[:, 0] + zz[:, 1:L + 1] * w[:, 1] + zz[:, 2:L + 2] * w[:, 2] + fir_b.to(z.dtype)
+    x2, x1, v = column_split(zp.permute(0, 2, 1), num_heads, head_dim)              # (B, D, L)
+    x1v = x1 * v
+    p = torch.view_as_complex(poles.to(torch.float64))[..., 0]
+    r = torch.view_as_complex(residues.to(torch.float64))[..., 0]
+    st = state_in.clone() if state_in is not None else torch.zeros(B, p.shape[0], p.shape[1], dtype=torch.complex128)
+    conv = torch.empty_like(x1v)
+    for t in range(L):
+        st = p[None] * st + x1v[:, :, t, None]
+        conv[:, :, t] = (r[None] * st).sum(-1).real
+    y = (conv + x1v * Dskip.to(z.dtype)[None, :, None]) * x2
+    return y.permute(0, 2, 1), st
