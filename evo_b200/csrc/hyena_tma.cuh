@@ -177,21 +177,45 @@ hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
   uint32_t* yrow = STATE_ONLY ? nullptr : reinterpret_cast<uint32_t*>(a.y + ((long long)b * a.L + t0) * a.D + ch);
   const long long ystride = a.D / 2;        // in 32-bit words
 
-  for (int k = 0; k < n_tiles; ++k) {
-    const int st = k % STAGES;
-    mbar_wait(&full[st], (uint32_t)(k / STAGES) & 1);
-    const uint8_t* tile = smem + st * STAGE_BYTES + hh * 3 * SUB_BYTES + j2 * 2;
-    const int n_tok = (int)min((long long)T2, t1 - (t0 + (long long)k * T2));
-#pragma unroll 4
-    for (int j = 0; j < T2; ++j) {
-      if (j < n_tok) {
-        const float2 z1 = unpack2(*reinterpret_cast<const uint32_t*>(tile + 1 * SUB_BYTES + j * 256));
-        const float2 zv = unpack2(*reinterpret_cast<const uint32_t*>(tile + 2 * SUB_BYTES + j * 256));
-        // short FIR: conv (fp32 accumulate, rp) then bias (rp)
-        float2 f1 = rbf2(__fadd2_rn(rbf2(__ffma2_rn(w1[2], z1, __ffma2_rn(w1[1], h1[1], __fmul2_rn(w1[0], h1[0])))), b1));
-        float2 fv = rbf2(__fadd2_rn(rbf2(__ffma2_rn(wv[2], zv, __ffma2_rn(wv[1], hv[1], __fmul2_rn(wv[0], hv[0])))), bv));
-        h1[0] = h1[1]; h1[1] = z1; hv[0] = hv[1]; hv[1] = zv;
-        const float2 x = rbf2(__fmul2_rn(f1, fv));               // x1v (rp)
+  // One group = G tokens.  The element-wise stages (FIR + roundings, output gating) have no
+  // cross-token dependence, so they are written as straight-line code over the group: a single
+  // in-order warp per SM sub-partition needs that ILP (there is no second warp to switch to).
+  // Only the 8-state recurrence in the middle is sequential in t.
+  constexpr int G = 8;
+  auto do_group = [&](const uint8_t* tile, int j0, int n_valid, uint32_t* ydst) {
+    uint32_t xq[G], f2q[G], ycq[G];
+    // ---- stage A: short FIR (fp32 accumulate, rp) + bias (rp); x = x1*v (rp)
+    float2 zin1[G], zinv[G], zin2[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      zin1[g] = unpack2(*reinterpret_cast<const uint32_t*>(tile + 1 * SUB_BYTES + (j0 + g) * 256));
+      zinv[g] = unpack2(*reinterpret_cast<const uint32_t*>(tile + 2 * SUB_BYTES + (j0 + g) * 256));
+      if (!STATE_ONLY) zin2[g] = unpack2(*reinterpret_cast<const uint32_t*>(tile + (j0 + g) * 256));
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float2 a1 = g >= 2 ? zin1[g - 2] : h1[g], b1_ = g >= 1 ? zin1[g - 1] : h1[1];
+      const float2 av = g >= 2 ? zinv[g - 2] : hv[g], bv_ = g >= 1 ? zinv[g - 1] : hv[1];
+      const float2 f1 = rbf2(__fadd2_rn(rbf2(__ffma2_rn(w1[2], zin1[g], __ffma2_rn(w1[1], b1_, __fmul2_rn(w1[0], a1)))), b1));
+      const float2 fv = rbf2(__fadd2_rn(rbf2(__ffma2_rn(wv[2], zinv[g], __ffma2_rn(wv[1], bv_, __fmul2_rn(wv[0], av)))), bv));
+      const float2 xx = __fmul2_rn(f1, fv);
+      xq[g] = pack_bf16(xx.x, xx.y);
+      if (!STATE_ONLY) {
+        const float2 a2 = g >= 2 ? zin2[g - 2] : h2[g], b2_ = g >= 1 ? zin2[g - 1] : h2[1];
+        const float2 f2 = __fadd2_rn(rbf2(__ffma2_rn(w2[2], zin2[g], __ffma2_rn(w2[1], b2_, __fmul2_rn(w2[0], a2)))), b2);
+        f2q[g] = pack_bf16(f2.x, f2.y);
+      }
+    }
+    // FIR history for the next group = last two valid inputs of this one
+    if (n_valid == G) {
+      h1[0] = zin1[G - 2]; h1[1] = zin1[G - 1]; hv[0] = zinv[G - 2]; hv[1] = zinv[G - 1];
+      if (!STATE_ONLY) { h2[0] = zin2[G - 2]; h2[1] = zin2[G - 1]; }
+    }
+    // ---- stage B: modal recurrence, sequential in t, 16 independent complex-pair chains per step
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (g < n_valid) {
+        const float2 x = unpack2(xq[g]);
         float2 accr = make_float2(0.f, 0.f), acci = make_float2(0.f, 0.f);
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -201,16 +225,34 @@ hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
           sr[s] = nr; si[s] = ni;
           if (!STATE_ONLY) { accr = __ffma2_rn(rr[s], nr, accr); acci = __ffma2_rn(ri[s], ni, acci); }
         }
-        if (!STATE_ONLY) {
-          const float2 z2 = unpack2(*reinterpret_cast<const uint32_t*>(tile + j * 256));
-          const float2 f2 = rbf2(__fadd2_rn(rbf2(__ffma2_rn(w2[2], z2, __ffma2_rn(w2[1], h2[1], __fmul2_rn(w2[0], h2[0])))), b2));
-          h2[0] = h2[1]; h2[1] = z2;
-          const float2 yc = rbf2(__fadd2_rn(accr, acci));         // y.to(bf16) (rp)
-          const float2 u = rbf2(__fadd2_rn(yc, rbf2(__fmul2_rn(x, dsk))));   // y + x1v*D (rp, rp)
-          const float2 o = __fmul2_rn(u, f2);                     // * x2 (rp on pack)
-          yrow[((long long)k * T2 + j) * ystride] = pack_bf16(o.x, o.y);
+        if (!STATE_ONLY) { const float2 c = __fadd2_rn(accr, acci); ycq[g] = pack_bf16(c.x, c.y); }   // y.to(bf16) (rp)
+      }
+    }
+    // ---- stage C: y = (conv + x1v*D) * x2 with the reference's roundings, bf16x2 stores
+    if (!STATE_ONLY) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (g < n_valid) {
+          const float2 x = unpack2(xq[g]);
+          const float2 u = rbf2(__fadd2_rn(unpack2(ycq[g]), rbf2(__fmul2_rn(x, dsk))));
+          const float2 o = __fmul2_rn(u, unpack2(f2q[g]));
+          ydst[(long long)g * ystride] = pack_bf16(o.x, o.y);
         }
       }
+    }
+  };
+
+  for (int k = 0; k < n_tiles; ++k) {
+    const int st = k % STAGES;
+    mbar_wait(&full[st], (uint32_t)(k / STAGES) & 1);
+    const uint8_t* tile = smem + st * STAGE_BYTES + hh * 3 * SUB_BYTES + j2 * 2;
+    const int n_tok = (int)min((long long)T2, t1 - (t0 + (long long)k * T2));
+    uint32_t* ytile = STATE_ONLY ? nullptr : yrow + (long long)k * T2 * ystride;
+    if (n_tok == T2) {
+#pragma unroll
+      for (int j0 = 0; j0 < T2; j0 += G) do_group(tile, j0, G, STATE_ONLY ? nullptr : ytile + (long long)j0 * ystride);
+    } else {                                   // ragged last tile of the segment
+      for (int j0 = 0; j0 < n_tok; j0 += G) do_group(tile, j0, min(G, n_tok - j0), STATE_ONLY ? nullptr : ytile + (long long)j0 * ystride);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);

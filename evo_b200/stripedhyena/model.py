@@ -28,7 +28,10 @@ from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID
 from .cache import InferenceParams, RecurrentInferenceParams
 
 # kernel variants (see include/evo_b200.h); overridable for experiments
-GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "1"))
+# measured on B200 (profiles/r01_perf_kernels_call3.jsonl): the 2-CTA 256x256 tile wins for the plain
+# epilogues, the 1-CTA 128x256 tile for the GELU-gate epilogue (its epilogue is the heavier one)
+GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "0"))
+GEMM_VARIANT_GATE = int(os.environ.get("EVO_B200_GEMM_VARIANT_GATE", "1"))
 ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "1"))
 
 
@@ -142,6 +145,7 @@ class StripedHyena(nn.Module):
         self._packed = None
         self._rope = None
         self.gemm_variant = GEMM_VARIANT
+        self.gemm_variant_gate = GEMM_VARIANT_GATE
         self.attn_variant = ATTN_VARIANT
         self._prof = None   # set to a list to record (kind, algorithmic work, start event, end event) per kernel call
 
@@ -221,7 +225,7 @@ class StripedHyena(nn.Module):
         p = GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=ldc or N,
                        bias=bias.data_ptr() if bias is not None else None,
                        residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
-                       M=M, N=N, K=K, epilogue=epi, variant=self.gemm_variant)
+                       M=M, N=N, K=K, epilogue=epi, variant=self.gemm_variant_gate if epi == EPI_GELU_GATE else self.gemm_variant)
         self._record("gemm", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
 
     def _rmsnorm(self, x, scale, out, rows):

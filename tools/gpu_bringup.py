@@ -306,7 +306,7 @@ def stage_model():
         cfg = O.tiny_config(num_layers=4, attn_layer_idxs=(1, 3), hidden_size=256, num_heads=2)
         sd = O.random_state_dict(cfg, seed=7)
         m = StripedHyena(dotdict(cfg)); m.load_state_dict(sd, strict=True); m.to_bfloat16_except_poles_residues(); m = m.to(dev)
-        m.gemm_variant, m.attn_variant = gv, av
+        m.gemm_variant, m.gemm_variant_gate, m.attn_variant = gv, gv, av
         ob = O.OracleStripedHyena(cfg, sd, torch.bfloat16); ot = O.OracleStripedHyena(cfg, sd, torch.float64)
         torch.manual_seed(0)
         ids = torch.randint(0, 4, (2, 333)) * 3 + 65
