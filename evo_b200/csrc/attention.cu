@@ -2,11 +2,13 @@
 // Replaces flash_attn_qkvpacked_func (flash_attn/modules/mha.py:122; FA2 = mma.sync HMMA
 // kernels recompiled for sm_100) with a tcgen05/TMEM kernel:
 //
-//   one CTA = 128 query rows of one (batch, head); 6 warps:
-//     warps 0-3  softmax + epilogue: thread r owns query row r == TMEM lane r, so the row
-//                max / sum need no shuffles (tcgen05.ld 32x32b)
-//     warp 4     TMA producer: Q once, K and V tiles (128 keys) through 2-deep mbarrier rings
-//     warp 5     MMA issuer: S = Q K^T (SS, 128x128x128) into one of two TMEM S buffers and
+//   one CTA = 128 query rows of one (batch, head); 10 warps:
+//     warps 0-7  softmax + epilogue: thread (q, lane) of column-half hf owns query row
+//                r = 32q + lane (== TMEM lane r) and 64 of the tile's 128 key columns, so a row
+//                needs no shuffles, only one smem exchange of the half-row max per tile; two
+//                warps per SM sub-partition hide the MUFU / TMEM / smem latencies of each other
+//     warp 8     TMA producer: Q once, K and V tiles (128 keys) through 2-deep mbarrier rings
+//     warp 9     MMA issuer: S = Q K^T (SS, 128x128x128) into one of two TMEM S buffers and
 //                O += P V (SS, P staged by the softmax warps in 128B-swizzled smem)
 //   S is double-buffered so Q K_{j+1}^T runs on the tensor pipe while the CUDA cores do
 //   softmax(j); O stays in TMEM across KV tiles and is rescaled lazily (only when the running
@@ -26,9 +28,13 @@ constexpr int BQ = 128;          // query rows per CTA
 constexpr int BKV = 128;         // keys per tile
 constexpr int TILE_BYTES = 128 * 128 * 2;          // any 128x128 bf16 tile = 2 x (128 rows x 64) swizzled halves
 constexpr int HALF_BYTES = TILE_BYTES / 2;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
+constexpr int SM_WARPS = 8;             // softmax warps; producer = warp 8, MMA = warp 9
 constexpr int KV_STAGES = 2;
-constexpr int ATT_SMEM = TILE_BYTES * (1 + 2 * KV_STAGES + 2) + 1024 + 256;   // Q + K ring + V ring + 2 P buffers
+// 7 tiles + barriers + max-exchange buffer = 226.25 KB of the 227 KB limit: the dynamic smem base is
+// declared 1024-aligned instead of padding for a manual round-up
+constexpr int ATT_SMEM = TILE_BYTES * (1 + 2 * KV_STAGES + 2) + 256 + 2 * 2 * 128 * 4;
+static_assert(ATT_SMEM <= 232448, "exceeds the 227 KB dynamic shared memory limit");   // Q + K ring + V ring + 2 P buffers
 constexpr uint32_t TM_S0 = 0, TM_O = 256;
 
 struct AttArgs {
@@ -57,8 +63,9 @@ template <bool V_MN>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;                                  // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();               // fail loudly, never compute on a misaligned tile
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + TILE_BYTES;
   uint8_t* sV = sK + KV_STAGES * TILE_BYTES;
@@ -74,6 +81,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = s_empty + 2;          // 2
   uint64_t* pv_done = p_full + 2;          // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xch = reinterpret_cast<float*>(bars + 32);          // [2 parities][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_qblk = (int)((a.Lq + BQ - 1) / BQ);
@@ -84,20 +92,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const long long last_key = min(a.Lk - 1, a.q_pos0 + q0 + BQ - 1);
   const int n_kv = (int)(last_key / BKV) + 1;
 
-  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
-  if (warp == 5 && lane == 0) {
+  if (warp == SM_WARPS && lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+  if (warp == SM_WARPS + 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&p_full[i], 128); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 32 * SM_WARPS); mbar_init(&p_full[i], 32 * SM_WARPS); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 5) { __syncwarp(); tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
+  if (warp == SM_WARPS + 1) { __syncwarp(); tmem_alloc<1>(tmem_slot, 512); tmem_relinquish<1>(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == SM_WARPS) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, TILE_BYTES);
@@ -122,7 +130,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == SM_WARPS + 1) {
     // ------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV);
@@ -163,53 +171,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    // ------------------------------------------------ softmax + epilogue (warps 0-3)
-    const int r = warp * 32 + lane;                         // query row in the block == TMEM lane
+    // ------------------------------------------------ softmax + epilogue (warps 0-7)
+    const int q = warp & 3, hf = warp >> 2;                 // TMEM lane quarter, key-column half
+    const int r = q * 32 + lane;                            // query row in the block == TMEM lane
     const long long pos = a.q_pos0 + q0 + r;                // absolute position of this query
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int HC = BKV / 2;                             // 64 columns per thread
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
-      float s[BKV];
-      {   // all four 32-column loads in flight, one wait
-        uint32_t t0[32], t1[32], t2[32], t3[32];
-        const uint32_t sa = lane_addr + TM_S0 + sb * BKV;
-        tmem_ld_32x32(sa, t0); tmem_ld_32x32(sa + 32, t1); tmem_ld_32x32(sa + 64, t2); tmem_ld_32x32(sa + 96, t3);
+      float s[HC];
+      {
+        uint32_t t0[32], t1[32];
+        const uint32_t sa = lane_addr + TM_S0 + sb * BKV + hf * HC;
+        tmem_ld_32x32(sa, t0); tmem_ld_32x32(sa + 32, t1);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s[i] = __uint_as_float(t0[i]); s[32 + i] = __uint_as_float(t1[i]);
-          s[64 + i] = __uint_as_float(t2[i]); s[96 + i] = __uint_as_float(t3[i]);
-        }
+        for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(t0[i]); s[32 + i] = __uint_as_float(t1[i]); }
       }
       tc_fence_before();
       mbar_arrive(&s_empty[sb]);
       // causal / length mask on tiles that reach past this row's position
-      const long long key0 = (long long)j * BKV;
-      if (key0 + BKV - 1 > pos) {
+      const long long key0 = (long long)j * BKV + hf * HC;
+      if (key0 + HC - 1 > pos) {
 #pragma unroll
-        for (int i = 0; i < BKV; ++i) if (key0 + i > pos) s[i] = -INFINITY;
+        for (int i = 0; i < HC; ++i) if (key0 + i > pos) s[i] = -INFINITY;
       }
-      // row max: 8 independent chains (a single warp per SMSP cannot hide a 128-long dependent chain)
       float mxs[8];
 #pragma unroll
       for (int q8 = 0; q8 < 8; ++q8) mxs[q8] = s[q8];
 #pragma unroll
-      for (int i = 8; i < BKV; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], s[i]);
+      for (int i = 8; i < HC; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], s[i]);
       float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])), fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
-      mx *= a.scale_log2;
+      // exchange the half-row max with the partner thread (same row, other column half)
+      float* xb = xch + (j & 1) * 256;
+      xb[hf * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xb[(hf ^ 1) * 128 + r]) * a.scale_log2;
       // lazy rescale: keep the old reference unless the max grew by more than 2^8
       float alpha = 1.f;
       bool grow = mx > m_ref + 8.f;
       if (j == 0) { m_ref = (mx == -INFINITY) ? 0.f : mx; grow = false; }
       else if (grow) { alpha = ex2(m_ref - mx); m_ref = mx; l *= alpha; }
-      // P = exp2(s*scale - m_ref), written as bf16 into the swizzled A-operand tile
-      uint8_t* prow = sP + sb * TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      // P = exp2(s*scale - m_ref), written as bf16 into this half of the swizzled A-operand tile
+      uint8_t* prow = sP + sb * TILE_BYTES + hf * HALF_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {                          // 16-byte chunks: 8 keys each
+      for (int c = 0; c < 8; ++c) {                           // 16-byte chunks: 8 keys each
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -218,25 +228,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           ls[i] += p0 + p1;
           w[i] = pack_bf16(p0, p1);
         }
-        uint8_t* dst = prow + (c >> 3) * HALF_BYTES + (((c & 7) ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      l += lsum;
-      // O rescale (warp-collective because tcgen05.ld/st are): needs PV(j-1) finished
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      // O rescale of this thread's 64 output columns (warp-collective because tcgen05.ld/st are)
       if (j > 0) {
         const bool any = __any_sync(0xffffffffu, grow);
         mbar_wait(&pv_done[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1);
         if (any) {
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < HD; c += 32) {
+          for (int c = 0; c < HC; c += 32) {
             uint32_t t[32];
-            tmem_ld_32x32(lane_addr + TM_O + c, t);
+            tmem_ld_32x32(lane_addr + TM_O + hf * HC + c, t);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-            tmem_st_32x32(lane_addr + TM_O + c, t);
+            tmem_st_32x32(lane_addr + TM_O + hf * HC + c, t);
           }
           tmem_st_wait();
           tc_fence_before();
@@ -245,15 +253,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async_smem();      // P (generic-proxy stores) -> visible to the tensor core's async proxy
       mbar_arrive(&p_full[sb]);
     }
-    // epilogue: O / l -> bf16 -> out[b, q0+r, h*128 : (h+1)*128]
+    // epilogue: O / l -> bf16 -> out[b, q0+r, h*128 + hf*64 : +64]; l = sum of both halves
+    float* xb = xch + (n_kv & 1) * 256;
+    xb[hf * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xb[(hf ^ 1) * 128 + r];
     mbar_wait(&pv_done[(n_kv - 1) & 1], (uint32_t)((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l;
-    bf16* orow = a.out + (((long long)b * a.Lq + q0 + r) * a.H + h) * HD;
+    bf16* orow = a.out + (((long long)b * a.Lq + q0 + r) * a.H + h) * HD + hf * HC;
 #pragma unroll 1
-    for (int c = 0; c < HD; c += 32) {
+    for (int c = 0; c < HC; c += 32) {
       uint32_t t[32];
-      tmem_ld_32x32(lane_addr + TM_O + c, t);
+      tmem_ld_32x32(lane_addr + TM_O + hf * HC + c, t);
       tmem_ld_wait();
       if (q0 + r < a.Lq) {
 #pragma unroll
@@ -272,7 +284,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<1>(tmem_base, 512);
+  if (warp == SM_WARPS + 1) tmem_dealloc<1>(tmem_base, 512);
 }
 
 // (B, L, H, 128) strided -> (B, H, 128, Lpad): 64x64 smem tile transpose

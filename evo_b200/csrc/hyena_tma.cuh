@@ -41,6 +41,7 @@ struct Args2 {
 
 __device__ __forceinline__ float2 unpack2(uint32_t v) { return make_float2(bf_lo(v), bf_hi(v)); }
 __device__ __forceinline__ float2 rbf2(float2 a) { return unpack2(pack_bf16(a.x, a.y)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ float2 ld_bf2(const bf16* p) { return unpack2(__ldg(reinterpret_cast<const unsigned int*>(p))); }
 
 struct C2 { float2 r, i; };                  // two complex numbers (one per channel of the pair)
@@ -182,15 +183,15 @@ hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
   // in-order warp per SM sub-partition needs that ILP (there is no second warp to switch to).
   // Only the 8-state recurrence in the middle is sequential in t.
   constexpr int G = 8;
-  auto do_group = [&](const uint8_t* tile, int j0, int n_valid, uint32_t* ydst) {
+  auto do_group = [&](uint32_t tile, int j0, int n_valid, uint32_t* ydst) {
     uint32_t xq[G], f2q[G], ycq[G];
     // ---- stage A: short FIR (fp32 accumulate, rp) + bias (rp); x = x1*v (rp)
     float2 zin1[G], zinv[G], zin2[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      zin1[g] = unpack2(*reinterpret_cast<const uint32_t*>(tile + 1 * SUB_BYTES + (j0 + g) * 256));
-      zinv[g] = unpack2(*reinterpret_cast<const uint32_t*>(tile + 2 * SUB_BYTES + (j0 + g) * 256));
-      if (!STATE_ONLY) zin2[g] = unpack2(*reinterpret_cast<const uint32_t*>(tile + (j0 + g) * 256));
+      zin1[g] = unpack2(lds32(tile + 1 * SUB_BYTES + (j0 + g) * 256));
+      zinv[g] = unpack2(lds32(tile + 2 * SUB_BYTES + (j0 + g) * 256));
+      if (!STATE_ONLY) zin2[g] = unpack2(lds32(tile + (j0 + g) * 256));
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -245,7 +246,7 @@ hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
   for (int k = 0; k < n_tiles; ++k) {
     const int st = k % STAGES;
     mbar_wait(&full[st], (uint32_t)(k / STAGES) & 1);
-    const uint8_t* tile = smem + st * STAGE_BYTES + hh * 3 * SUB_BYTES + j2 * 2;
+    const uint32_t tile = smem_u32(smem) + st * STAGE_BYTES + hh * 3 * SUB_BYTES + j2 * 2;
     const int n_tok = (int)min((long long)T2, t1 - (t0 + (long long)k * T2));
     uint32_t* ytile = STATE_ONLY ? nullptr : yrow + (long long)k * T2 * ystride;
     if (n_tok == T2) {

@@ -10,8 +10,11 @@ work (embedding, RMSNorm, every GEMM, the gated MLP, unembed) needs no communica
                    (B, D, 8) complex64 -> ONE all-gather of 256 KB*B per rank -> every rank folds
                    S_in = sum_{q<r} p^{(r-1-q) Lr} E_q (evo_hyena_combine_states) and runs the
                    output scan from S_in.  Exact: it is the modal recurrence itself.
-  Attention layer  K and V of earlier shards are all-gathered (bf16, 2*Lr*D per rank); rank r
-                   attends its Lr queries over keys [0, (r+1) Lr).
+  Attention layer  head <-> sequence re-shard (Ulysses): one all-to-all turns the local
+                   (Lr tokens x H heads) qkv into (L tokens x H/P heads), every rank runs the
+                   full-length causal kernel for its heads (perfectly balanced: a K/V all-gather
+                   would leave the last rank with 1.9x the average causal work), a second
+                   all-to-all returns the context to sequence-sharded layout.
 """
 from __future__ import annotations
 
@@ -29,6 +32,37 @@ def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
     out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t.contiguous(), group=group)
     return out
+
+
+def _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, stream):
+    """qkv (B*Lr, 3*H*hd) rotary-applied, sequence-sharded -> ctx (B*Lr, H*hd), sequence-sharded."""
+    if H % world != 0:
+        raise _lib.EvoError(f"sequence-parallel attention needs heads ({H}) divisible by the world size ({world})")
+    Hl = H // world
+    dev = qkv.device
+    L = Lr * world
+    # (B, Lr, 3, P, Hl, hd) -> (P, B, Lr, 3, Hl, hd): chunk p goes to rank p
+    send = qkv.view(B, Lr, 3, world, Hl, hd).permute(3, 0, 1, 2, 4, 5).contiguous()
+    recv = torch.empty_like(send)                     # (P = source rank = sequence chunk, B, Lr, 3, Hl, hd)
+    dist.all_to_all_single(recv, send, group=group)
+    if B == 1:
+        full = recv.view(1, L, 3, Hl, hd)             # source-rank order is sequence order
+    else:
+        full = recv.permute(1, 0, 2, 3, 4, 5).reshape(B, L, 3, Hl, hd).contiguous()
+    dl = Hl * hd
+    out = torch.empty(B, L, dl, dtype=torch.bfloat16, device=dev)
+    ap = AttnParams(out=out.data_ptr(), B=B, Lq=L, Lk=L, H=Hl, hd=hd, q_pos0=0, softmax_scale=1.0 / math.sqrt(hd))
+    ap.q, ap.q_tok_stride, ap.q_batch_stride = full.data_ptr(), 3 * dl, L * 3 * dl
+    ap.k, ap.v, ap.kv_tok_stride, ap.kv_batch_stride = full.data_ptr() + dl * 2, full.data_ptr() + 2 * dl * 2, 3 * dl, L * 3 * dl
+    n = lib.evo_attn_fwd_workspace(C.byref(ap), model.attn_variant)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    causal_flops = 4.0 * B * Hl * hd * (L * (L + 1) / 2.0)
+    model._record("attn", causal_flops, lambda: check(lib.evo_attn_fwd_ws(C.byref(ap), model.attn_variant, ptr(ws), n, stream()), "evo_attn_fwd"))
+    # back: (B, P, Lr, Hl*hd) -> chunk p (its tokens, my heads) to rank p
+    send2 = out.view(B, world, Lr, dl).permute(1, 0, 2, 3).contiguous()
+    recv2 = torch.empty_like(send2)                   # (P = head group, B, Lr, dl)
+    dist.all_to_all_single(recv2, send2, group=group)
+    ctx.view(B, Lr, world, dl).copy_(recv2.permute(1, 2, 0, 3))
 
 
 def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: int, group=None):
@@ -59,18 +93,8 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 cos, sin = model._rope_tables(pos0 + Lr, dev)
                 check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + pos0 * (hd // 2) * 2), C.c_void_p(sin.data_ptr() + pos0 * (hd // 2) * 2),
                                         B, Lr, H, hd, stream()), "evo_rotary_qk")
-                kv_local = qkv.view(B, Lr, 3, d)[:, :, 1:].contiguous()                    # (B, Lr, 2, D)
-                kv_all = _all_gather(kv_local, world, group)                               # (W, B, Lr, 2, D)
-                Lk = (rank + 1) * Lr
-                kv = kv_all[: rank + 1].permute(1, 0, 2, 3, 4).reshape(B, Lk, 2 * d)
-                kv = kv if kv.is_contiguous() else kv.contiguous()
                 ctx = xn
-                ap = AttnParams(out=ctx.data_ptr(), B=B, Lq=Lr, Lk=Lk, H=H, hd=hd, q_pos0=pos0, softmax_scale=1.0 / math.sqrt(hd))
-                ap.q, ap.q_tok_stride, ap.q_batch_stride = qkv.data_ptr(), 3 * d, Lr * 3 * d
-                ap.k, ap.v, ap.kv_tok_stride, ap.kv_batch_stride = kv.data_ptr(), kv.data_ptr() + d * 2, 2 * d, Lk * 2 * d
-                n = lib.evo_attn_fwd_workspace(C.byref(ap), model.attn_variant)
-                ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
-                check(lib.evo_attn_fwd_ws(C.byref(ap), model.attn_variant, ptr(ws), n, stream()), "evo_attn_fwd")
+                _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, stream)
                 u2 = torch.empty_like(u)
                 model._gemm(ctx, mha.out_proj.weight, u2, M, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID, bias=mha.out_proj.bias, resid=u)
             else:
@@ -86,7 +110,7 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                                  force_segments=0, state_only=1)
                 n = lib.evo_hyena_fwd_workspace(C.byref(hp))
                 ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
-                check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), n, stream()), "evo_hyena_fwd(state)")
+                model._record("hyena_state", 4.0 * B * Lr * d, lambda: check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), n, stream()), "evo_hyena_fwd(state)"))
                 ends = _all_gather(end, world, group)                                      # (W, B, D, S, 2)
                 s_in = torch.empty_like(end)
                 check(lib.evo_hyena_combine_states(ptr(ends), ptr(s_in), ptr(f.poles), rank, world, Lr, B, d, S, stream()), "evo_hyena_combine_states")
@@ -94,7 +118,7 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 hp.y, hp.state_in, hp.state_out, hp.state_only = y.data_ptr(), s_in.data_ptr(), None, 0
                 n2 = lib.evo_hyena_fwd_workspace(C.byref(hp))
                 ws2 = torch.empty(max(n2, 1), dtype=torch.uint8, device=dev)
-                check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws2), n2, stream()), "evo_hyena_fwd")
+                model._record("hyena", 8.0 * B * Lr * d, lambda: check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws2), n2, stream()), "evo_hyena_fwd"))
                 u2 = torch.empty_like(u)
                 model._gemm(y, blk.out_filter_dense.weight, u2, M, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u)
             u = model._mlp_residual(i, blk, u2, M)

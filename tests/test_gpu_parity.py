@@ -29,7 +29,7 @@ from tools import gpu_bringup as G                    # noqa: E402  (shared laun
 
 G._imports()
 DEV = "cuda:0"
-BF16_EPS = 2.0 ** -8
+BF16_EPS = 2.0 ** -7      # one bf16 ulp relative to the magnitude (8 significand bits)
 
 
 @pytest.fixture(scope="module", autouse=True)

@@ -1,7 +1,8 @@
 """N > 1 path on CPU: two gloo ranks run the sequence-sharded Hyena algebra of
 evo_b200/parallel.py (halo exchange + zero-start end states -> all-gather -> fold with
 p^(shard length) -> output scan from the folded state) with the oracle's time-domain operator
-and must reproduce the unsharded result; plus the K/V all-gather form of causal attention."""
+and must reproduce the unsharded result; plus the head<->sequence all-to-all (Ulysses) form
+of causal attention."""
 import os
 import socket
 
@@ -50,15 +51,22 @@ def _worker(rank, world, port, q):
         err = (y_loc - y_full[:, rank * Lr:(rank + 1) * Lr]).abs().max().item()
         st_err = (st_loc - st_full).abs().max().item() if rank == world - 1 else 0.0
 
-        # attention: rank r attends its queries over the all-gathered keys [0, (r+1) Lr)
-        qkv = torch.randn(B, L, 3, 2, 16, dtype=torch.float64)
+        # attention: head <-> sequence re-shard (Ulysses), as evo_b200/parallel.py does it
+        Hh, dh = 2 * world, 16
+        qkv = torch.randn(B, L, 3, Hh, dh, dtype=torch.float64)
         ref = O.causal_attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2])
-        kv_l = qkv[:, rank * Lr:(rank + 1) * Lr, 1:].contiguous()
-        kvs = [torch.empty_like(kv_l) for _ in range(world)]
-        dist.all_gather(kvs, kv_l)
-        kv = torch.cat(kvs[: rank + 1], dim=1)
-        out = O.causal_attention(qkv[:, rank * Lr:(rank + 1) * Lr, 0], kv[:, :, 0], kv[:, :, 1], q_offset=rank * Lr)
-        a_err = (out - ref[:, rank * Lr:(rank + 1) * Lr]).abs().max().item()
+        Hl = Hh // world
+        loc = qkv[:, rank * Lr:(rank + 1) * Lr]                                        # (B, Lr, 3, H, d)
+        send = loc.reshape(B, Lr, 3, world, Hl, dh).permute(3, 0, 1, 2, 4, 5).contiguous()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        full = recv.permute(1, 0, 2, 3, 4, 5).reshape(B, L, 3, Hl, dh)                 # my heads, whole sequence
+        o = O.causal_attention(full[:, :, 0], full[:, :, 1], full[:, :, 2])            # (B, L, Hl, d)
+        send2 = o.reshape(B, world, Lr, Hl * dh).permute(1, 0, 2, 3).contiguous()
+        recv2 = torch.empty_like(send2)
+        dist.all_to_all_single(recv2, send2)
+        mine = recv2.permute(1, 2, 0, 3).reshape(B, Lr, Hh, dh)
+        a_err = (mine - ref[:, rank * Lr:(rank + 1) * Lr]).abs().max().item()
         q.put((rank, err, st_err, a_err))
     finally:
         dist.destroy_process_group()
