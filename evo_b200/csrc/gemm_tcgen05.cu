@@ -23,18 +23,19 @@ using namespace evo;
 namespace {
 
 constexpr int BM = 128;            // rows of C per CTA
-constexpr int BN = 256;            // columns of C per tile (UMMA N)
+constexpr int BN_BIG = 256;        // columns of C per tile (UMMA N) for the throughput tiles
+constexpr int BN_SMALL = 64;       // weight-streaming tiles for small M (decode): N/64 CTAs keep every SM pulling HBM
 constexpr int BK = 64;             // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UK = 16;             // UMMA K for 16-bit inputs
 constexpr int NTHREADS = 256;
 constexpr int EPI_WARP0 = 4;
 
-template <int CG> struct Cfg {
+template <int CG, int BN> struct Cfg {
   static constexpr int B_ROWS = BN / CG;                       // W rows staged per CTA
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CG == 1 ? 4 : 6;
+  static constexpr int STAGES = BN == BN_SMALL ? 8 : (CG == 1 ? 4 : 6);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -105,10 +106,11 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& g, long long row, in
   for (int q = 0; q < 4; ++q) dst[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
 }
 
-template <int CG, int EPI>
+template <int CG, int EPI, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  using C_ = Cfg<CG>;
+  using C_ = Cfg<CG, BN>;
+  static_assert(EPI != EVO_EPI_GELU_GATE || BN == BN_BIG, "the gate epilogue needs [l1 | l2] halves of a 256-column tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
@@ -130,7 +132,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CG); }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc<CG>(tmem_slot, 512); tmem_relinquish<CG>(); }
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers (power of two >= 32)
+  if (warp == 2) { tmem_alloc<CG>(tmem_slot, TMEM_COLS); tmem_relinquish<CG>(); }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -203,7 +206,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
-      if constexpr (EPI == EVO_EPI_GELU_GATE) {
+      if constexpr (EPI == EVO_EPI_GELU_GATE && BN == BN_BIG) {
 #pragma unroll 1
         for (int c = 0; c < BN / 2; c += 32) {
           uint32_t r1[32], r2[32];
@@ -231,12 +234,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncwarp();            // single-lane roles rejoin their warp before the aligned barriers
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
 }
 
-template <int CG, int EPI>
+template <int CG, int EPI, int BN>
 int launch(const evo_gemm_params* p, cudaStream_t st) {
-  using C_ = Cfg<CG>;
+  using C_ = Cfg<CG, BN>;
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda * 2, BK, BM, true))) return rc;
@@ -248,7 +251,7 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   g.n_blocks = (int)(p->N / BN);
   g.group_m = CG == 1 ? 16 : 8;
   static bool attr_done = false;
-  auto kern = gemm_tcgen05_kernel<CG, EPI>;
+  auto kern = gemm_tcgen05_kernel<CG, EPI, BN>;
   if (!attr_done) {
     EVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
     attr_done = true;
@@ -273,14 +276,16 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   return check_launch("evo_gemm");
 }
 
-template <int CG>
+template <int CG, int BN>
 int dispatch_epi(const evo_gemm_params* p, cudaStream_t st) {
   switch (p->epilogue) {
-    case EVO_EPI_NONE: return launch<CG, EVO_EPI_NONE>(p, st);
-    case EVO_EPI_BIAS: return launch<CG, EVO_EPI_BIAS>(p, st);
-    case EVO_EPI_BIAS_RESID: return launch<CG, EVO_EPI_BIAS_RESID>(p, st);
-    case EVO_EPI_RESID: return launch<CG, EVO_EPI_RESID>(p, st);
-    case EVO_EPI_GELU_GATE: return launch<CG, EVO_EPI_GELU_GATE>(p, st);
+    case EVO_EPI_NONE: return launch<CG, EVO_EPI_NONE, BN>(p, st);
+    case EVO_EPI_BIAS: return launch<CG, EVO_EPI_BIAS, BN>(p, st);
+    case EVO_EPI_BIAS_RESID: return launch<CG, EVO_EPI_BIAS_RESID, BN>(p, st);
+    case EVO_EPI_RESID: return launch<CG, EVO_EPI_RESID, BN>(p, st);
+    case EVO_EPI_GELU_GATE:
+      if constexpr (BN == BN_BIG) return launch<CG, EVO_EPI_GELU_GATE, BN>(p, st);
+      else { set_error("evo_gemm: the GELU-gate epilogue is not available on the small-M tile (variant 2)"); return -1; }
   }
   set_error("evo_gemm: unknown epilogue %d", p->epilogue);
   return -1;
@@ -291,13 +296,14 @@ int dispatch_epi(const evo_gemm_params* p, cudaStream_t st) {
 extern "C" int evo_gemm(const evo_gemm_params* p, void* stream) {
   EVO_REQUIRE(p->M >= 0 && p->N > 0 && p->K > 0, "evo_gemm: bad shape");
   EVO_REQUIRE(p->K % BK == 0, "evo_gemm: K (%lld) must be a multiple of %d", (long long)p->K, BK);
-  EVO_REQUIRE(p->N % BN == 0, "evo_gemm: N (%lld) must be a multiple of %d (pack weights at load time)", (long long)p->N, BN);
+  EVO_REQUIRE(p->N % BN_BIG == 0, "evo_gemm: N (%lld) must be a multiple of %d (pack weights at load time)", (long long)p->N, BN_BIG);
   EVO_REQUIRE(p->lda % 8 == 0 && p->ldc % 8 == 0, "evo_gemm: lda/ldc must be multiples of 8 elements");
   EVO_REQUIRE(((uintptr_t)p->A % 16) == 0 && ((uintptr_t)p->W % 16) == 0 && ((uintptr_t)p->C % 16) == 0, "evo_gemm: pointers must be 16-byte aligned");
   if (p->epilogue == EVO_EPI_BIAS || p->epilogue == EVO_EPI_BIAS_RESID) EVO_REQUIRE(p->bias != nullptr, "evo_gemm: bias epilogue without bias");
   if (p->epilogue == EVO_EPI_RESID || p->epilogue == EVO_EPI_BIAS_RESID)
     EVO_REQUIRE(p->residual != nullptr && p->ldr % 8 == 0 && ((uintptr_t)p->residual % 16) == 0, "evo_gemm: residual epilogue without a valid residual");
   if (p->M == 0) return 0;
-  if (p->variant == 1) return dispatch_epi<1>(p, (cudaStream_t)stream);
-  return dispatch_epi<2>(p, (cudaStream_t)stream);
+  if (p->variant == 2) return dispatch_epi<1, BN_SMALL>(p, (cudaStream_t)stream);
+  if (p->variant == 1) return dispatch_epi<1, BN_BIG>(p, (cudaStream_t)stream);
+  return dispatch_epi<2, BN_BIG>(p, (cudaStream_t)stream);
 }

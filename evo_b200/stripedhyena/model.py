@@ -147,6 +147,8 @@ class StripedHyena(nn.Module):
         self.gemm_variant = GEMM_VARIANT
         self.gemm_variant_gate = GEMM_VARIANT_GATE
         self.attn_variant = ATTN_VARIANT
+        self.decode_graph = os.environ.get("EVO_B200_DECODE_GRAPH", "1") != "0"
+        self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
         self._prof = None   # set to a list to record (kind, algorithmic work, start event, end event) per kernel call
 
     # ---- reference API ------------------------------------------------------------------
@@ -168,12 +170,14 @@ class StripedHyena(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._packed = None
+        self._decode = None
         return out
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
         self._packed = None
         self._rope = None
+        self._decode = None
         return out
 
     # ---- weight packing (once per load / move) ---------------------------------------------
@@ -221,11 +225,13 @@ class StripedHyena(nn.Module):
         e1.record()
         self._prof.append((kind, work, e0, e1))
 
-    def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None):
+    def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None, variant=None):
+        if variant is None:
+            variant = self.gemm_variant_gate if epi == EPI_GELU_GATE else self.gemm_variant
         p = GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=ldc or N,
                        bias=bias.data_ptr() if bias is not None else None,
                        residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
-                       M=M, N=N, K=K, epilogue=epi, variant=self.gemm_variant_gate if epi == EPI_GELU_GATE else self.gemm_variant)
+                       M=M, N=N, K=K, epilogue=epi, variant=variant)
         self._record("gemm", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
 
     def _rmsnorm(self, x, scale, out, rows):
@@ -360,6 +366,9 @@ class StripedHyena(nn.Module):
         M = B * L
         d = self.config.hidden_size
         V = self.config.vocab_size
+        if L == 1 and inference_params_dict is not None and self._can_step(inference_params_dict, B):
+            with torch.cuda.device(dev), torch.no_grad():
+                return self._decode_forward(x, inference_params_dict), inference_params_dict
         with torch.cuda.device(dev), torch.no_grad():
             u = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
             check(_lib.lib().evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u),
@@ -378,3 +387,109 @@ class StripedHyena(nn.Module):
             logits = torch.empty(M, V, dtype=torch.bfloat16, device=dev)
             self._gemm(u, self.unembed.weight, logits, M, V, d, EPI_NONE)
         return logits.view(B, L, V), inference_params_dict
+
+    # ---- decode step: small-M weight-streaming GEMM tiles + device-side position + CUDA graph ------
+    def _can_step(self, ipd, B):
+        mha, hy = ipd["mha"], ipd["hyena"]
+        for i in range(len(self.blocks)):
+            if i in self._attn_idxs:
+                c = mha.key_value_memory_dict.get(i)
+                if c is None or c.shape[0] < B:
+                    return False
+            elif i not in hy.fir_state_dict or i not in hy.state_dict:
+                return False
+        return True
+
+    def _decode_body(self, x, pos_dev, ipd, B):
+        """One token per sequence through all blocks; every launch reads the position from pos_dev."""
+        cfg = self.config
+        d, H, V = cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size
+        hd = d // H
+        dev = x.device
+        lib = _lib.lib()
+        mha_ip, hy_ip = ipd["mha"], ipd["hyena"]
+        G2 = 2  # weight-streaming tile variant
+        u = torch.empty(B, d, dtype=torch.bfloat16, device=dev)
+        check(lib.evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u), B, d, V, self._stream()), "evo_embed")
+        nsplit = max(1, min(16, -(-2 * torch.cuda.get_device_properties(dev).multi_processor_count // (H * B))))
+        for i, blk in enumerate(self.blocks):
+            xn = torch.empty_like(u)
+            self._rmsnorm(u, blk.pre_norm.scale, xn, B)
+            u2 = torch.empty_like(u)
+            if i in self._attn_idxs:
+                mha = blk.inner_mha_cls
+                qkv = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
+                self._gemm(xn, mha.Wqkv.weight, qkv, B, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias, variant=G2)
+                cache = mha_ip.key_value_memory_dict[i]
+                cos, sin = self._rope_tables(cache.shape[1], dev)
+                check(lib.evo_decode_qkv_prep(ptr(qkv), ptr(cache), ptr(cos), ptr(sin), ptr(pos_dev), B, H, hd, cache.shape[1], self._stream()), "evo_decode_qkv_prep")
+                nws = lib.evo_decode_attn_workspace(B, H, nsplit)
+                ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+                ctx = xn
+                check(lib.evo_decode_attn(ptr(qkv), ptr(cache), ptr(ctx), ptr(pos_dev), B, H, hd, cache.shape[1], nsplit,
+                                          1.0 / math.sqrt(hd), ptr(ws), nws, self._stream()), "evo_decode_attn")
+                self._gemm(ctx, mha.out_proj.weight, u2, B, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID,
+                           bias=mha.out_proj.bias, resid=u, variant=G2)
+            else:
+                f = blk.filter
+                z = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
+                self._gemm(xn, blk.projections.weight, z, B, 3 * d, d, EPI_BIAS, bias=blk.projections.bias, variant=G2)
+                y = xn
+                check(lib.evo_hyena_step(ptr(z), ptr(y), ptr(hy_ip.fir_state_dict[i]), ptr(torch.view_as_real(hy_ip.state_dict[i])),
+                                         ptr(f.short_filter_weight), ptr(f.short_filter_bias), ptr(f.D), ptr(f.poles), ptr(f.residues),
+                                         B, d, cfg.state_size, H, self._stream()), "evo_hyena_step")
+                self._gemm(y, blk.out_filter_dense.weight, u2, B, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u, variant=G2)
+            pk = self._packed[i]
+            xn2 = xn
+            self._rmsnorm(u2, blk.post_norm.scale, xn2, B)
+            t = torch.empty(B, 2 * pk["ipad"], dtype=torch.bfloat16, device=dev)
+            self._gemm(xn2, pk["w12"], t, B, 2 * pk["ipad"], d, EPI_NONE, variant=G2)
+            g = torch.empty(B, pk["ipad"], dtype=torch.bfloat16, device=dev)
+            check(lib.evo_gelu_gate_interleaved(ptr(t), ptr(g), B, pk["ipad"], self._stream()), "evo_gelu_gate_interleaved")
+            u = torch.empty_like(u2)
+            self._gemm(g, pk["w3"], u, B, d, pk["ipad"], EPI_RESID, resid=u2, variant=G2)
+        if self.norm is not None:
+            xn = torch.empty_like(u)
+            self._rmsnorm(u, self.norm.scale, xn, B)
+            u = xn
+        logits = torch.empty(B, V, dtype=torch.bfloat16, device=dev)
+        self._gemm(u, self.unembed.weight, logits, B, V, d, EPI_NONE, variant=G2)
+        return logits
+
+    def _decode_forward(self, x, ipd):
+        """L == 1 with populated states.  Step 1 after a prefill runs eagerly (and makes the state
+        tensors contiguous / resident); step 2 captures the whole step into a CUDA graph; later
+        steps replay it: one host call per token instead of ~15 launches per block."""
+        mha_ip, hy_ip = ipd["mha"], ipd["hyena"]
+        dev = x.device
+        B = x.shape[0]
+        for i in list(hy_ip.state_dict):
+            if not hy_ip.state_dict[i].is_contiguous():
+                hy_ip.state_dict[i] = hy_ip.state_dict[i].contiguous()
+            if not hy_ip.fir_state_dict[i].is_contiguous():
+                hy_ip.fir_state_dict[i] = hy_ip.fir_state_dict[i].contiguous()
+        key = (B, x.dtype, tuple(hy_ip.state_dict[i].data_ptr() for i in sorted(hy_ip.state_dict)),
+               tuple(hy_ip.fir_state_dict[i].data_ptr() for i in sorted(hy_ip.fir_state_dict)),
+               tuple(mha_ip.key_value_memory_dict[i].data_ptr() for i in sorted(mha_ip.key_value_memory_dict)))
+        off = int(mha_ip.seqlen_offset)
+        for i in mha_ip.key_value_memory_dict:
+            if off >= mha_ip.key_value_memory_dict[i].shape[1]:
+                raise _lib.EvoError(f"sequence length {off + 1} exceeds the KV cache ({mha_ip.key_value_memory_dict[i].shape[1]}) (mha.py:367)")
+        st = self._decode
+        if st is None or st["key"] != key:
+            st = {"key": key, "graph": None, "x": torch.empty_like(x), "pos": torch.zeros(1, dtype=torch.int64, device=dev), "logits": None, "steps": 0}
+            self._decode = st
+        st["pos"].fill_(off)
+        st["x"].copy_(x)
+        if not self.decode_graph or self._prof is not None or st["steps"] == 0:
+            st["steps"] += 1
+            return self._decode_body(st["x"], st["pos"], ipd, B).view(B, 1, -1)
+        if st["graph"] is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                st["logits"] = self._decode_body(st["x"], st["pos"], ipd, B)
+            st["graph"] = g
+        st["graph"].replay()
+        st["steps"] += 1
+        return st["logits"].clone().view(B, 1, -1)

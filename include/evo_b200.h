@@ -62,7 +62,7 @@ typedef struct {
   const void* residual; int64_t ldr;
   int64_t M, N, K;
   int epilogue;
-  int variant;                   /* 0 = default (2-CTA pairs); 1 = single-CTA tiles */
+  int variant;                   /* 0 = 2-CTA 256x256 tiles; 1 = 1-CTA 128x256 tiles; 2 = 1-CTA 128x64 weight-streaming tiles (small M) */
 } evo_gemm_params;
 int evo_gemm(const evo_gemm_params* p, void* stream);
 /* test comparator only (cuBLASLt, plain C = A.W^T [+bias]); never on the product path */
@@ -137,6 +137,21 @@ int evo_attn_fwd_simple(const evo_attn_params* p, void* stream);
  * (max_B, max_seqlen, 2, H, hd) bf16 — MHA._update_kv_cache (mha.py:344-370). */
 int evo_kv_append(const void* qkv, void* cache, int B, int64_t L, int H, int hd,
                   int64_t pos0, int64_t max_seqlen, void* stream);
+
+/* ---- decode step (L == 1), CUDA-graph friendly: the sequence position is read from DEVICE memory ----
+ * evo_gelu_gate_interleaved: out[m, g*128+c] = bf16(gelu(t[m, g*256+c])) * t[m, g*256+128+c]; t (M, 2*ipad) is the
+ *   plain GEMM output against the [l1 | l2]-interleaved weights (small-M tiles have no fused gate epilogue).
+ * evo_decode_qkv_prep: rotary on q,k of qkv (B, 3, H, 128) at position *pos and append of k,v at cache row *pos
+ *   (flash_attn_with_kvcache's rotary + cache-append half, mha.py:502-540).
+ * evo_decode_attn: one query per sequence over cache keys [0, *pos] (the attention half); split-K over nsplit.
+ * evo_advance_position: *pos += delta on the stream. */
+int evo_gelu_gate_interleaved(const void* t, void* out, int64_t M, int ipad, void* stream);
+int evo_decode_qkv_prep(void* qkv, void* cache, const void* cos, const void* sin, const int64_t* pos,
+                        int B, int H, int hd, int64_t max_seqlen, void* stream);
+size_t evo_decode_attn_workspace(int B, int H, int nsplit);
+int evo_decode_attn(const void* qkv, const void* cache, void* out, const int64_t* pos, int B, int H, int hd,
+                    int64_t max_seqlen, int nsplit, float softmax_scale, void* workspace, size_t workspace_bytes, void* stream);
+int evo_advance_position(int64_t* pos, int64_t delta, void* stream);
 
 /* ---- elementwise glue kept for completeness / tests ---- */
 int evo_add(const void* a, const void* b, void* out, int64_t n, void* stream);

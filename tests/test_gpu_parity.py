@@ -227,9 +227,11 @@ def test_hyena_full_size_properties():
 
 
 # ------------------------------------------------------------------ tensor-core linear layers
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 0, 2])
 @pytest.mark.parametrize("M,N,K", [(1, 256, 64), (128, 256, 64), (300, 512, 256), (1000, 768, 256), (4096, 4096, 4096), (8200, 512, 1024)])
 def test_gemm_all_epilogues(variant, M, N, K):
+    if variant == 2 and M > 1000:
+        pytest.skip("variant 2 is the small-M weight-streaming tile")
     torch.manual_seed(M + N)
     a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
     w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
@@ -252,7 +254,14 @@ def test_gemm_all_epilogues(variant, M, N, K):
     z1 = (a.double() @ wv[:, 0].reshape(-1, K).double().T).bfloat16()
     z2 = (a.double() @ wv[:, 1].reshape(-1, K).double().T).bfloat16()
     ref = (torch.nn.functional.gelu(z1.float()).bfloat16().float() * z2.float()).bfloat16()
-    out = G._gemm(a, w, M, N, K, _lib.EPI_GELU_GATE, variant, ldc=N // 2)
+    if variant == 2:      # no fused gate on the small-M tile: plain GEMM + evo_gelu_gate_interleaved (decode path)
+        with pytest.raises(_lib.EvoError):
+            G._gemm(a, w, M, N, K, _lib.EPI_GELU_GATE, variant, ldc=N // 2)
+        t = G._gemm(a, w, M, N, K, _lib.EPI_NONE, variant)
+        out = torch.empty(M, N // 2, dtype=torch.bfloat16, device=DEV)
+        _lib.check(_lib.lib().evo_gelu_gate_interleaved(_lib.ptr(t), _lib.ptr(out), M, N // 2, stream()))
+    else:
+        out = G._gemm(a, w, M, N, K, _lib.EPI_GELU_GATE, variant, ldc=N // 2)
     assert maxerr(out, ref) <= 2 * BF16_EPS * max(1.0, ref.abs().max().item())
     assert (out == ref).float().mean() > (0.97 if K <= 1024 else 0.88)
 
@@ -314,6 +323,37 @@ def test_attention_kv_cache_form(variant):
         q = full[:, off:off + Lq].contiguous().to(DEV)
         o = G._attn(q, B, Lq, H, variant, cache=cd, off=off)
         assert maxerr(o, ref[:, off:off + Lq]) <= 4 * BF16_EPS * max(1.0, ref.abs().max().item())
+
+
+def test_decode_attention_with_device_position():
+    """evo_decode_qkv_prep + evo_decode_attn (position read from device memory) vs the oracle."""
+    B, H, Lc = 3, 2, 640
+    lib = _lib.lib()
+    torch.manual_seed(9)
+    full = torch.randn(B, 600, 3, H, 128).bfloat16()
+    cos, sin = O.rotary_tables(Lc, 128, dtype=torch.bfloat16)
+    q = O.apply_rotary(full[:, :, 0], cos[:600], sin[:600])
+    k = O.apply_rotary(full[:, :, 1], cos[:600], sin[:600])
+    ref = O.causal_attention(q, k, full[:, :, 2]).reshape(B, 600, H * 128)
+    cache = torch.zeros(B + 1, Lc, 2, H, 128, dtype=torch.bfloat16)
+    cosd, sind = cos.to(DEV), sin.to(DEV)
+    for pos in (0, 1, 130, 599):
+        cache[:B, :pos, 0] = k[:, :pos]
+        cache[:B, :pos, 1] = full[:, :pos, 2]
+        cd = cache.to(DEV)
+        qkv = full[:, pos].contiguous().to(DEV)                       # (B, 3, H, 128), un-rotated
+        posd = torch.tensor([pos], dtype=torch.int64, device=DEV)
+        _lib.check(lib.evo_decode_qkv_prep(_lib.ptr(qkv), _lib.ptr(cd), _lib.ptr(cosd), _lib.ptr(sind), _lib.ptr(posd), B, H, 128, Lc, stream()))
+        assert (cd[:B, pos, 0].cpu() == k[:, pos]).float().mean() > 0.995 and torch.equal(cd[:B, pos, 1].cpu(), full[:, pos, 2])
+        for nsplit in (1, 4):
+            n = lib.evo_decode_attn_workspace(B, H, nsplit)
+            ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+            out = torch.empty(B, H * 128, dtype=torch.bfloat16, device=DEV)
+            _lib.check(lib.evo_decode_attn(_lib.ptr(qkv), _lib.ptr(cd), _lib.ptr(out), _lib.ptr(posd), B, H, 128, Lc, nsplit,
+                                           1 / math.sqrt(128), _lib.ptr(ws), n, stream()))
+            assert maxerr(out, ref[:, pos]) <= 4 * BF16_EPS * max(1.0, ref.abs().max().item())
+    _lib.check(lib.evo_advance_position(_lib.ptr(posd), 3, stream()))
+    assert posd.item() == 602
 
 
 def test_attention_full_length_8193_vs_cuda_core_comparator():

@@ -385,6 +385,39 @@ def stage_perf_attn():
                 emit("perf_attn", B=B, L=L, variant="flash_attn2_library", error=str(e)[:200])
 
 
+def stage_perf_decode():
+    """BASELINE configs[3]: evo-1.5-8k-base generate, batch 16, prompt 4096 + decode (recurrent state path)."""
+    from evo_b200.models import load_checkpoint
+    dev = "cuda:0"
+    m = load_checkpoint("evo-1.5-8k-base", device=dev, random_init=True, seed=0)
+    B, P, N = 16, 4096, 96
+    g = torch.Generator().manual_seed(0)
+    ids = (torch.randint(0, 4, (B, P + N), generator=g) * 3 + 65).to(dev)
+    d = m.initialize_inference_params()
+    d["mha"].max_batch_size = B
+    d["hyena"].max_batch_size = B
+    torch.cuda.synchronize(); t0 = time.time()
+    lg, d = m(ids[:, :P], inference_params_dict=d)
+    torch.cuda.synchronize(); t_prefill = time.time() - t0
+    d["mha"].seqlen_offset = d["hyena"].seqlen_offset = P
+    outs = []
+    times = []
+    for t in range(P, P + N):
+        torch.cuda.synchronize(); t0 = time.time()
+        s, d = m(ids[:, t:t + 1], inference_params_dict=d)
+        torch.cuda.synchronize(); times.append(time.time() - t0)
+        outs.append(s[:, 0])
+        d["mha"].seqlen_offset += 1; d["hyena"].seqlen_offset += 1
+    steady = sorted(times[8:])[len(times[8:]) // 2]
+    # sanity: teacher-forced decode logits vs one stateless forward over the same P+N tokens (last 8 positions)
+    full, _ = m(ids[:2, :P + N])
+    dec = torch.stack(outs, 1)[:2]
+    e = (dec[:, -8:].float() - full[:, P + N - 8:].float()).abs()
+    emit("perf_decode", B=B, prompt=P, steps=N, prefill_s=t_prefill, prefill_nt_s=B * P / t_prefill, first_step_ms=times[0] * 1e3, capture_step_ms=times[1] * 1e3,
+         steady_ms_per_step=steady * 1e3, decode_nt_s=B / steady, decode_vs_stateless_max=e.max().item(), logit_scale=full.float().abs().max().item(),
+         weight_stream_floor_ms=12.9e9 / 6566.4e9 * 1e3)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", default=None)
@@ -397,4 +430,4 @@ if __name__ == "__main__":
         _imports()
         {"elementwise": stage_elementwise, "hyena": stage_hyena, "gemm1": lambda: stage_gemm(1), "gemm2": lambda: stage_gemm(0),
          "attn0": lambda: stage_attn(0), "attn1": lambda: stage_attn(1), "model": stage_model, "perf_gemm": stage_perf_gemm,
-         "perf_hyena": stage_perf_hyena, "perf_attn": stage_perf_attn}[a.stage]()
+         "perf_hyena": stage_perf_hyena, "perf_attn": stage_perf_attn, "perf_decode": stage_perf_decode}[a.stage]()
