@@ -28,7 +28,7 @@ class HyenaParams(C.Structure):
                 ("poles", C.c_void_p), ("residues", C.c_void_p),
                 ("B", C.c_int), ("L", C.c_int64), ("D", C.c_int), ("S", C.c_int), ("nheads", C.c_int),
                 ("halo", C.c_void_p), ("state_in", C.c_void_p), ("state_out", C.c_void_p), ("fir_state_out", C.c_void_p),
-                ("force_segments", C.c_int), ("state_only", C.c_int)]
+                ("force_segments", C.c_int), ("state_only", C.c_int), ("reuse_segment_states", C.c_int)]
 
 
 class AttnParams(C.Structure):

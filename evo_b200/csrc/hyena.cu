@@ -337,7 +337,7 @@ extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t 
       hyena_scan_tma_kernel<true><<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
       if ((rc = check_launch("hyena_scan_tma<state>"))) return rc;
     } else {
-      if (nseg > 1) {
+      if (nseg > 1 && !p->reuse_segment_states) {
         dim3 g2(grid.x, grid.y, nseg - 1);
         hyena_scan_tma_kernel<true><<<g2, block, SMEM_BYTES, st>>>(tmZ, a);
         if ((rc = check_launch("hyena_scan_tma<state>"))) return rc;
@@ -359,7 +359,7 @@ extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t 
       hyena_scan_kernel<true><<<grid, block, 0, st>>>(a);
       if ((rc = check_launch("hyena_scan<state>"))) return rc;
     } else {
-      if (nseg > 1) {
+      if (nseg > 1 && !p->reuse_segment_states) {
         dim3 g2(grid.x, grid.y, nseg - 1);     // the last segment's zero-start state is never needed
         hyena_scan_kernel<true><<<g2, block, 0, st>>>(a);
         if ((rc = check_launch("hyena_scan<state>"))) return rc;

@@ -115,10 +115,9 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 s_in = torch.empty_like(end)
                 check(lib.evo_hyena_combine_states(ptr(ends), ptr(s_in), ptr(f.poles), rank, world, Lr, B, d, S, stream()), "evo_hyena_combine_states")
                 y = xn
-                hp.y, hp.state_in, hp.state_out, hp.state_only = y.data_ptr(), s_in.data_ptr(), None, 0
-                n2 = lib.evo_hyena_fwd_workspace(C.byref(hp))
-                ws2 = torch.empty(max(n2, 1), dtype=torch.uint8, device=dev)
-                model._record("hyena", 8.0 * B * Lr * d, lambda: check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws2), n2, stream()), "evo_hyena_fwd"))
+                # output pass: same geometry, so the per-segment end states of the carry pass are reused from `ws`
+                hp.y, hp.state_in, hp.state_out, hp.state_only, hp.reuse_segment_states = y.data_ptr(), s_in.data_ptr(), None, 0, 1
+                model._record("hyena", 8.0 * B * Lr * d, lambda: check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), n, stream()), "evo_hyena_fwd"))
                 u2 = torch.empty_like(u)
                 model._gemm(y, blk.out_filter_dense.weight, u2, M, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u)
             u = model._mlp_residual(i, blk, u2, M)

@@ -28,9 +28,10 @@ from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID
 from .cache import InferenceParams, RecurrentInferenceParams
 
 # kernel variants (see include/evo_b200.h); overridable for experiments
-# measured on B200 (profiles/r01_perf_kernels_call3.jsonl): the 2-CTA 256x256 tile wins for the plain
-# epilogues, the 1-CTA 128x256 tile for the GELU-gate epilogue (its epilogue is the heavier one)
-GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "0"))
+# measured on B200: in isolated bursts the 2-CTA 256x256 tile is the faster one for the plain epilogues
+# (profiles/r01_perf_kernels_call3.jsonl), but inside the power-capped 0.8 s step the 1-CTA 128x256 tile
+# sustains ~2 % more (profiles/r01_bench_8k_variants_call5.json, same box back to back)
+GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "1"))
 GEMM_VARIANT_GATE = int(os.environ.get("EVO_B200_GEMM_VARIANT_GATE", "1"))
 ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "1"))
 

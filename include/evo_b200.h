@@ -90,6 +90,8 @@ typedef struct {
   float* state_out; void* fir_state_out;
   int force_segments;            /* 0 = auto; >0 forces the number of L segments (tests) */
   int state_only;                /* 1 = compute state_out only (sequence-parallel carry pass); y may be NULL */
+  int reuse_segment_states;      /* 1 = workspace already holds the zero-start segment end states of a preceding
+                                    state_only call on the same z / halo / geometry: skip recomputing them */
 } evo_hyena_params;
 size_t evo_hyena_fwd_workspace(const evo_hyena_params* p);
 int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t workspace_bytes, void* stream);
