@@ -50,6 +50,16 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(pattern, workload):
+    """Average DRAM bytes per launch of the kernels matching `pattern`, from the committed ncu --set full
+    capture of this workload (profiles/ncu_traffic_<workload>.json, made by tools/ncu_traffic.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", f"ncu_traffic_{workload}.json")
+    if not os.path.exists(path):
+        return None
+    rows = [r for r in json.load(open(path))["launches"] if pattern in r["kernel"]]
+    return sum(r["dram_bytes"] for r in rows) / len(rows) if rows else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -229,17 +239,19 @@ def bench_ours(args, wl):
         if "gemm" in by:
             ach = by["gemm"][0] / (by["gemm"][1] / 1e3) / 1e12
             roof["roofline"] = {"kernel": "gemm_tcgen05_kernel (all linear layers)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic("gemm_tcgen05", args.workload),
+                                "algorithmic_flops_per_launch": by["gemm"][0] / by["gemm"][2],
                                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "share_of_step": by["gemm"][1] / ms, "launches_per_step": by["gemm"][2] / steps}
         if "hyena" in by:
             ach = by["hyena"][0] / (by["hyena"][1] / 1e3) / 1e9
-            roof["roofline_hyena"] = {"kernel": "hyena_scan_kernel (fused FIR + gate + modal long conv + gate)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-                                      "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+            roof["roofline_hyena"] = {"kernel": "hyena_scan_tma_kernel (fused FIR + gate + modal long conv + gate)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                                      "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic("hyena_scan", args.workload),
+                                      "algorithmic_bytes_per_launch": by["hyena"][0] / by["hyena"][2], "peak_source": peaks["source"],
                                       "share_of_step": by["hyena"][1] / ms, "launches_per_step": by["hyena"][2] / steps}
         if "attn" in by:
             ach = by["attn"][0] / (by["attn"][1] / 1e3) / 1e12
             roof["roofline_attn"] = {"kernel": "attn_fwd_kernel (tcgen05 causal attention)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic("attn_fwd", args.workload),
                                      "share_of_step": by["attn"][1] / ms, "launches_per_step": by["attn"][2] / steps}
         out = {
             "metric": "nucleotides/sec forward, evo-1 7B", "value": value, "unit": "nt/s", "n_gpus": world, "steps": steps, "warmup": warmup,

@@ -217,16 +217,20 @@ hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
     for (int g = 0; g < G; ++g) {
       if (g < n_valid) {
         const float2 x = unpack2(xq[g]);
-        float2 accr = make_float2(0.f, 0.f), acci = make_float2(0.f, 0.f);
+        // four short accumulation chains instead of two 8-long ones (FFMA2 latency is exposed: one warp per SMSP)
+        float2 ar0 = make_float2(0.f, 0.f), ar1 = ar0, ai0 = ar0, ai1 = ar0;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
           const float2 t_ = __ffma2_rn(npi[s], si[s], x);
           const float2 nr = __ffma2_rn(pr[s], sr[s], t_);
           const float2 ni = __ffma2_rn(pr[s], si[s], __fmul2_rn(pi[s], sr[s]));
           sr[s] = nr; si[s] = ni;
-          if (!STATE_ONLY) { accr = __ffma2_rn(rr[s], nr, accr); acci = __ffma2_rn(ri[s], ni, acci); }
+          if (!STATE_ONLY) {
+            if (s & 1) { ar1 = __ffma2_rn(rr[s], nr, ar1); ai1 = __ffma2_rn(ri[s], ni, ai1); }
+            else       { ar0 = __ffma2_rn(rr[s], nr, ar0); ai0 = __ffma2_rn(ri[s], ni, ai0); }
+          }
         }
-        if (!STATE_ONLY) { const float2 c = __fadd2_rn(accr, acci); ycq[g] = pack_bf16(c.x, c.y); }   // y.to(bf16) (rp)
+        if (!STATE_ONLY) { const float2 c = __fadd2_rn(__fadd2_rn(ar0, ar1), __fadd2_rn(ai0, ai1)); ycq[g] = pack_bf16(c.x, c.y); }   // y.to(bf16) (rp)
       }
     }
     // ---- stage C: y = (conv + x1v*D) * x2 with the reference's roundings, bf16x2 stores

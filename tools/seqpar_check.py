@@ -25,7 +25,7 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=torch.device(dev))
     out = {}
-    for name, cfg, B, L in (("tiny4", O.tiny_config(num_layers=4, attn_layer_idxs=(1, 3), hidden_size=256, num_heads=2), 2, 1024 * world),
+    for name, cfg, B, L in (("tiny4", O.tiny_config(num_layers=4, attn_layer_idxs=(1, 3), hidden_size=128 * max(2, world), num_heads=max(2, world)), 2, 1024 * world),
                             ("wide2_131k_rope", dict(O.evo_config("evo-1-131k-base"), num_layers=2, attn_layer_idxs=[1], hyena_layer_idxs=[0]), 1, 2048 * world)):
         sd = O.random_state_dict(cfg, seed=5)
         m = StripedHyena(dotdict(cfg))
