@@ -418,3 +418,68 @@ extern "C" int evo_hyena_combine_states(const float* ends, float* state_in, cons
   combine_states_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ends, state_in, poles, rank, seg_len, B, D);
   return check_launch("evo_hyena_combine_states");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Sequence-parallel carry exchange over NVLink peer memory (no NCCL on the Hyena layers).
+// Every rank owns a symmetric buffer set; a rank PUSHES its data into its slot of every peer's
+// buffer with plain stores through the NVLink aperture, then raises a per-sender flag on the
+// peer (release at system scope); consumers spin on their local flags (acquire) inside the
+// kernel that needs the data, so the transfer overlaps whatever else the stream is doing and
+// costs no collective launch.  Flags carry a monotonically increasing epoch.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int* p) { int v; asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+__device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) < epoch) {
+    __nanosleep(64);
+    if (++spins > (1u << 28)) __trap();     // ~20 s: a peer died; fail loudly instead of hanging the box
+  }
+}
+
+// copy `n16` 16-byte words from src into slot `rank` of each destination in dsts[first..last], then flag
+__global__ void peer_publish_kernel(const uint4* __restrict__ src, long long n16, uint4* const* __restrict__ dsts, int* const* __restrict__ flags,
+                                    long long slot_stride16, int rank, int first, int last, int epoch, int* __restrict__ block_counter) {
+  for (int p = first; p <= last; ++p) {
+    uint4* d = dsts[p] + (long long)rank * slot_stride16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) d[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int prev = atomicAdd(block_counter, 1);
+    if (prev == (int)gridDim.x - 1) {
+      *block_counter = 0;
+      __threadfence_system();
+      for (int p = first; p <= last; ++p) st_release_sys(flags[p] + rank, epoch);
+    }
+  }
+}
+
+__global__ void wait_flags_kernel(const int* __restrict__ flags, int first, int last, int epoch) {
+  int q = first + threadIdx.x;
+  if (q <= last) wait_flag(flags + q, epoch);
+}
+
+}  // namespace
+
+extern "C" int evo_peer_publish(const void* src, int64_t bytes, void* const* peer_dsts, int* const* peer_flags, int64_t slot_stride_bytes,
+                                int rank, int first_peer, int last_peer, int epoch, int* block_counter, void* stream) {
+  EVO_REQUIRE(bytes % 16 == 0 && slot_stride_bytes % 16 == 0, "evo_peer_publish: sizes must be multiples of 16 bytes");
+  if (first_peer > last_peer) return 0;
+  long long n16 = bytes / 16;
+  int blocks = (int)std::min<long long>(64, std::max<long long>(1, (n16 + 255) / 256));
+  peer_publish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)src, n16, (uint4* const*)peer_dsts, peer_flags, slot_stride_bytes / 16,
+                                                               rank, first_peer, last_peer, epoch, block_counter);
+  return check_launch("evo_peer_publish");
+}
+
+extern "C" int evo_peer_wait(const int* flags, int first, int last, int epoch, void* stream) {
+  if (first > last) return 0;
+  EVO_REQUIRE(last - first < 64, "evo_peer_wait: too many peers");
+  wait_flags_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(flags, first, last, epoch);
+  return check_launch("evo_peer_wait");
+}

@@ -34,6 +34,40 @@ def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
     return out
 
 
+class PeerCarry:
+    """Symmetric (peer-mapped) buffers for the Hyena halo / end-state exchange: a ring of NBUF slot sets,
+    each [ends: world x end_bytes | halo: halo_bytes | end_flags: world x i32 | halo_flags: world x i32].
+    Ranks push with evo_peer_publish (NVLink stores + release flag) and consume after evo_peer_wait."""
+    NBUF = 8
+
+    def __init__(self, world, rank, B, d, S, dev, group):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = world, rank
+        self.end_bytes = B * d * S * 2 * 4
+        self.halo_bytes = B * 2 * 3 * d * 2
+        al = lambda n: (n + 255) // 256 * 256
+        self.off_halo = al(world * self.end_bytes)
+        self.off_eflag = self.off_halo + al(self.halo_bytes)
+        self.off_hflag = self.off_eflag + al(world * 4)
+        self.set_bytes = self.off_hflag + al(world * 4)
+        self.buf = symm.empty(self.NBUF * self.set_bytes, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
+        torch.cuda.synchronize(dev)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        mk = lambda vals: torch.tensor(vals, dtype=torch.int64, device=dev)
+        self.ends_dsts = [mk([p + k * self.set_bytes for p in ptrs]) for k in range(self.NBUF)]
+        self.halo_dsts = [mk([p + k * self.set_bytes + self.off_halo for p in ptrs]) for k in range(self.NBUF)]
+        self.eflag_dsts = [mk([p + k * self.set_bytes + self.off_eflag for p in ptrs]) for k in range(self.NBUF)]
+        self.hflag_dsts = [mk([p + k * self.set_bytes + self.off_hflag for p in ptrs]) for k in range(self.NBUF)]
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch = 0
+        self.key = (world, rank, B, d, S, str(dev))
+
+    def local(self, k, off, nbytes):
+        return self.buf[k * self.set_bytes + off: k * self.set_bytes + off + nbytes]
+
+
 def _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, stream):
     """qkv (B*Lr, 3*H*hd) rotary-applied, sequence-sharded -> ctx (B*Lr, H*hd), sequence-sharded."""
     if H % world != 0:
@@ -65,9 +99,11 @@ def _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, s
     ctx.view(B, Lr, world, dl).copy_(recv2.permute(1, 2, 0, 3))
 
 
-def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: int, group=None):
+def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: int, group=None, transport: str = "auto"):
     """ids_local: (B, L/world) slice `rank` of the token ids.  Returns the logits of the slice,
-    (B, L/world, V) bf16.  Stateless (scoring) forward only."""
+    (B, L/world, V) bf16.  Stateless (scoring) forward only.
+    transport: how the Hyena halo / end states travel: "peer" = pushed into peer-mapped symmetric memory by
+    our own kernels over NVLink, "nccl" = two all-gathers per layer, "auto" = peer when available."""
     model._ensure_packed()
     cfg = model.config
     lib = _lib.lib()
@@ -78,6 +114,21 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
     hd = d // H
     S = cfg.state_size
     stream = model._stream
+    pc = None
+    if transport in ("auto", "peer") and world > 1:
+        pc = getattr(model, "_peer_carry", None)
+        if pc is None or pc.key != (world, rank, B, d, S, str(dev)):
+            try:
+                pc = PeerCarry(world, rank, B, d, S, dev, group)
+            except Exception as ex:  # symmetric memory unavailable on this system
+                if transport == "peer":
+                    raise
+                pc = None
+                model._peer_carry_error = repr(ex)
+            model._peer_carry = pc
+        if pc is not None:
+            dist.barrier(group)          # nobody is still reading ring slots of the previous forward
+    since_sync = 0
     with torch.cuda.device(dev), torch.no_grad():
         ids_local = ids_local.contiguous()
         u = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
@@ -95,14 +146,31 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                                         B, Lr, H, hd, stream()), "evo_rotary_qk")
                 ctx = xn
                 _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, stream)
+                since_sync = 0           # the all-to-all is a global synchronisation point
                 u2 = torch.empty_like(u)
                 model._gemm(ctx, mha.out_proj.weight, u2, M, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID, bias=mha.out_proj.bias, resid=u)
             else:
                 f = blk.filter
                 z = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
                 model._gemm(xn, blk.projections.weight, z, M, 3 * d, d, EPI_BIAS, bias=blk.projections.bias)
-                tails = _all_gather(z.view(B, Lr, 3 * d)[:, -2:], world, group)            # (W, B, 2, 3D)
-                halo = tails[rank - 1].contiguous() if rank > 0 else None
+                tail = z.view(B, Lr, 3 * d)[:, -2:].contiguous()
+                if pc is not None:
+                    if since_sync == pc.NBUF:
+                        dist.barrier(group)
+                        since_sync = 0
+                    k = since_sync
+                    since_sync += 1
+                    pc.epoch += 1
+                    if rank + 1 < world:
+                        check(lib.evo_peer_publish(ptr(tail), pc.halo_bytes, ptr(pc.halo_dsts[k]), ptr(pc.hflag_dsts[k]), 0, rank, rank + 1, rank + 1,
+                                                   pc.epoch, ptr(pc.counter), stream()), "evo_peer_publish(halo)")
+                    halo = None
+                    if rank > 0:
+                        check(lib.evo_peer_wait(ptr(pc.local(k, pc.off_hflag, world * 4)), rank - 1, rank - 1, pc.epoch, stream()), "evo_peer_wait(halo)")
+                        halo = pc.local(k, pc.off_halo, pc.halo_bytes)
+                else:
+                    tails = _all_gather(tail, world, group)                                   # (W, B, 2, 3D)
+                    halo = tails[rank - 1].contiguous() if rank > 0 else None
                 end = torch.empty(B, d, S, 2, dtype=torch.float32, device=dev)
                 hp = HyenaParams(z=z.data_ptr(), y=None, fir_w=f.short_filter_weight.data_ptr(), fir_b=f.short_filter_bias.data_ptr(), Dskip=f.D.data_ptr(),
                                  poles=f.poles.data_ptr(), residues=f.residues.data_ptr(), B=B, L=Lr, D=d, S=S, nheads=H,
@@ -111,7 +179,15 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 n = lib.evo_hyena_fwd_workspace(C.byref(hp))
                 ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
                 model._record("hyena_state", 4.0 * B * Lr * d, lambda: check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), n, stream()), "evo_hyena_fwd(state)"))
-                ends = _all_gather(end, world, group)                                      # (W, B, D, S, 2)
+                if pc is not None:
+                    if rank + 1 < world:   # only later shards need my end state
+                        check(lib.evo_peer_publish(ptr(end), pc.end_bytes, ptr(pc.ends_dsts[k]), ptr(pc.eflag_dsts[k]), pc.end_bytes, rank, rank + 1, world - 1,
+                                                   pc.epoch, ptr(pc.counter), stream()), "evo_peer_publish(end)")
+                    if rank > 0:
+                        check(lib.evo_peer_wait(ptr(pc.local(k, pc.off_eflag, world * 4)), 0, rank - 1, pc.epoch, stream()), "evo_peer_wait(end)")
+                    ends = pc.local(k, 0, world * pc.end_bytes)
+                else:
+                    ends = _all_gather(end, world, group)                                  # (W, B, D, S, 2)
                 s_in = torch.empty_like(end)
                 check(lib.evo_hyena_combine_states(ptr(ends), ptr(s_in), ptr(f.poles), rank, world, Lr, B, d, S, stream()), "evo_hyena_combine_states")
                 y = xn

@@ -108,6 +108,15 @@ int evo_hyena_step(const void* u, void* y, void* fir_state, float* state,
 int evo_hyena_combine_states(const float* ends, float* state_in, const float* poles,
                              int rank, int nranks, int64_t seg_len, int B, int D, int S, void* stream);
 
+/* ---- peer-memory exchange for the sequence-parallel Hyena carry (NVLink stores + flags, no collective):
+ * evo_peer_publish copies `bytes` from src into slot `rank` (slot_stride_bytes apart) of each peer buffer
+ * peer_dsts[first_peer..last_peer] (device array of peer-mapped pointers) and then sets peer_flags[p][rank] = epoch
+ * with system-scope release; evo_peer_wait blocks the stream until flags[first..last] >= epoch (acquire).
+ * block_counter: one zero-initialised int of scratch on the calling device. */
+int evo_peer_publish(const void* src, int64_t bytes, void* const* peer_dsts, int* const* peer_flags, int64_t slot_stride_bytes,
+                     int rank, int first_peer, int last_peer, int epoch, int* block_counter, void* stream);
+int evo_peer_wait(const int* flags, int first, int last, int epoch, void* stream);
+
 /* ---- rotary tables + application (flash_attn layers/rotary.py:382-416,
  * ops/triton/rotary.py; stripedhyena LinearlyScaledRotaryEmbedding for 131k) ----
  * cos/sin (n_pos, hd/2) bf16 for positions pos0 .. pos0+n_pos-1, angle = (pos/scaling) * inv_freq[i]. */

@@ -36,14 +36,20 @@ def main():
         ids = (torch.randint(0, 4, (B, L), generator=g) * 3 + 65).to(dev)
         full, _ = m(ids)
         Lr = L // world
-        mine = sequence_parallel_forward(m, ids[:, rank * Lr:(rank + 1) * Lr].contiguous(), rank, world)
         ref = full[:, rank * Lr:(rank + 1) * Lr]
-        d = (mine.float() - ref.float()).abs()
-        stats = torch.tensor([d.max().item(), d.mean().item(), ref.float().abs().max().item(),
-                              (mine.argmax(-1) == ref.argmax(-1)).float().mean().item()], device=dev, dtype=torch.float64)
-        allst = [torch.empty_like(stats) for _ in range(world)]
-        dist.all_gather(allst, stats)
-        out[name] = [[float(v) for v in s.tolist()] for s in allst]
+        for transport in ("nccl", "peer"):
+            try:
+                mine = sequence_parallel_forward(m, ids[:, rank * Lr:(rank + 1) * Lr].contiguous(), rank, world, transport=transport)
+                mine2 = sequence_parallel_forward(m, ids[:, rank * Lr:(rank + 1) * Lr].contiguous(), rank, world, transport=transport)   # ring reuse
+                d = torch.maximum((mine.float() - ref.float()).abs(), (mine2.float() - ref.float()).abs())
+                stats = torch.tensor([d.max().item(), d.mean().item(), ref.float().abs().max().item(),
+                                      (mine.argmax(-1) == ref.argmax(-1)).float().mean().item()], device=dev, dtype=torch.float64)
+            except Exception as ex:  # noqa
+                print(f"[rank {rank}] transport {transport} failed: {ex!r}", flush=True)
+                stats = torch.tensor([float("nan")] * 4, device=dev, dtype=torch.float64)
+            allst = [torch.empty_like(stats) for _ in range(world)]
+            dist.all_gather(allst, stats)
+            out[f"{name}/{transport}"] = [[float(v) for v in s.tolist()] for s in allst]
     if rank == 0:
         print(json.dumps({"seqpar_check": out, "world": world, "cols": ["max_abs", "mean_abs", "ref_max", "argmax_agree"]}))
     dist.barrier()
