@@ -95,15 +95,31 @@ class ClockSampler:
 
 def cpu_baseline(model_name, target_seconds=15.0, threads=None):
     """Oracle (restatement of the reference, kind 'port') timed on the host cores on a bounded
-    sample: batch 1 x L_s tokens of the same 7B forward, L_s sized for ~target_seconds."""
+    sample: batch 1 x L_s tokens of the same 7B forward, L_s sized for ~target_seconds.
+    The reference keeps bf16 parameters on CPU too (evo/models.py:148), but host CPUs without
+    AMX / AVX512-BF16 run bf16 GEMMs through a slow path (measured: 0.7 nt/s on a 128-core GPU
+    host), so the arm first times one projection-sized GEMM in bf16 and fp32 and runs the forward
+    in the faster dtype, with the thread count that GEMM prefers; both choices are reported."""
     import torch
     from oracle import stripedhyena_oracle as O
-    threads = threads or os.cpu_count()
+    import numpy as np
+    ncpu = os.cpu_count() or 1
+
+    def gemm_time(dtype, nthreads):
+        torch.set_num_threads(nthreads)
+        a, w = torch.randn(128, 4096).to(dtype), torch.randn(12288, 4096).to(dtype)
+        torch.nn.functional.linear(a, w)
+        t0 = time.perf_counter()
+        torch.nn.functional.linear(a, w)
+        return time.perf_counter() - t0
+
+    cands = [(dt, nt) for dt in (torch.bfloat16, torch.float32) for nt in sorted({threads or ncpu, min(ncpu, 32)})]
+    timed = sorted((gemm_time(dt, nt), str(dt), dt, nt) for dt, nt in cands)
+    t_gemm, _, dtype, threads = timed[0]
     torch.set_num_threads(threads)
     cfg = O.evo_config(model_name)
     sd = O.random_state_dict(cfg, seed=0, share_blocks=True)   # blocks alias one set of weights: same arithmetic, small RAM
-    m = O.OracleStripedHyena(cfg, sd, torch.bfloat16)
-    import numpy as np
+    m = O.OracleStripedHyena(cfg, sd, dtype)
     rng = np.random.default_rng(0)
 
     def run(L):
@@ -114,12 +130,15 @@ def cpu_baseline(model_name, target_seconds=15.0, threads=None):
         return time.perf_counter() - t0
 
     run(16)                      # warm-up (thread pools, oneDNN primitives)
-    t_probe = run(64)
-    L = int(max(64, min(2048, 64 * target_seconds / max(t_probe, 1e-3))))
-    L = max(64, (L // 64) * 64)
-    t = run(L)
-    return {"value": L / t, "unit": "nt/s", "cores": threads, "kind": "port",
-            "sample": f"oracle (stripedhyena 0.2.2 restatement) bf16 on CPU, 7B shape, batch 1 x {L} nt, {t:.1f} s"}, m, run
+    t16 = run(16)                # measured probe: size the sample from a real forward, not from a model
+    if t16 >= target_seconds / 2:
+        L, t = 16, t16
+    else:
+        L = int(min(2048, 16 * target_seconds / t16))
+        L = max(32, (L // 32) * 32)
+        t = run(L)
+    return {"value": L / t, "unit": "nt/s", "cores": threads, "kind": "port", "host_cpus": ncpu, "cpu_dtype": str(dtype).replace("torch.", ""),
+            "sample": f"oracle (stripedhyena 0.2.2 restatement) {str(dtype).replace('torch.', '')} on CPU, 7B shape, batch 1 x {L} nt, {t:.1f} s"}, m, run
 
 
 def bench_reference(args, wl):

@@ -17,6 +17,9 @@
 // bf16 before the residual add / the gate): see include/evo_b200.h.
 #include "common.cuh"
 #include "../../include/evo_b200.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 using namespace evo;
 
@@ -45,19 +48,23 @@ struct GemmArgs {
   const bf16* resid; long long ldr;
   long long M, N, K;
   int m_blocks, n_blocks, group_m;
+  int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // grouped rasterisation: GROUP_M row-blocks share the sweep over n so their A tiles stay in L2
 __device__ __forceinline__ void tile_coords(int tile, const GemmArgs& g, int& m_blk, int& n_blk) {
-  int per_group = g.group_m * g.n_blocks;
+  const int major = g.raster_n ? g.n_blocks : g.m_blocks;     // the grouped dimension
+  const int minor = g.raster_n ? g.m_blocks : g.n_blocks;     // the swept dimension
+  int per_group = g.group_m * minor;
   int grp = tile / per_group;
-  int first_m = grp * g.group_m;
-  int gm = min(g.group_m, g.m_blocks - first_m);
+  int first = grp * g.group_m;
+  int gsz = min(g.group_m, major - first);
   int in = tile - grp * per_group;
-  m_blk = first_m + in % gm;
-  n_blk = in / gm;
+  int a = first + in % gsz, b = in / gsz;
+  m_blk = g.raster_n ? b : a;
+  n_blk = g.raster_n ? a : b;
 }
 
 template <int EPI>
@@ -249,7 +256,24 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.m_blocks = (int)((p->M + BM * CG - 1) / (BM * CG));
   g.n_blocks = (int)(p->N / BN);
-  g.group_m = CG == 1 ? 16 : 8;
+  // Rasterisation: keep the smaller operand slab resident in L2 while the other one streams.
+  //   grouped along M: GM row-blocks (GM * rows * K * 2 bytes of A) stay hot, W streams once per group;
+  //   grouped along N: GN column-blocks of W stay hot, A streams once per group.
+  // Pick the variant with the lower DRAM traffic estimate for a ~40 MB resident slab.
+  {
+    const double a_blk = (double)BM * CG * p->K * 2, w_blk = (double)BN * p->K * 2;
+    const double a_tot = (double)p->M * p->K * 2, w_tot = (double)p->N * p->K * 2, budget = 40e6;
+    int gm = (int)std::max(1.0, std::min((double)g.m_blocks, budget / a_blk));
+    int gn = (int)std::max(1.0, std::min((double)g.n_blocks, budget / w_blk));
+    const double traffic_m = a_tot + w_tot * std::ceil((double)g.m_blocks / gm);
+    const double traffic_n = w_tot + a_tot * std::ceil((double)g.n_blocks / gn);
+    g.raster_n = traffic_n < traffic_m;
+    g.group_m = g.raster_n ? gn : gm;
+    static const char* env_g = getenv("EVO_B200_GEMM_GROUP");      // experiments only
+    static const char* env_r = getenv("EVO_B200_GEMM_RASTER_N");
+    if (env_r) g.raster_n = atoi(env_r);
+    if (env_g) g.group_m = std::max(1, atoi(env_g));
+  }
   static bool attr_done = false;
   auto kern = gemm_tcgen05_kernel<CG, EPI, BN>;
   if (!attr_done) {
