@@ -38,8 +38,11 @@ template <int CG, int BN> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == BN_SMALL ? 8 : (CG == 1 ? 4 : 6);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // Small-M tile: A is staged COMPACT (only a_rows <= 128 rows per k-block; the MMA still reads a 128-row tile whose
+  // remaining rows alias later stages / padding and only feed accumulator rows that are never stored), which leaves
+  // room for a 16-deep ring of W tiles: bytes in flight, not tensor throughput, bound the weight-streaming GEMM.
+  static constexpr int STAGES = BN == BN_SMALL ? 16 : (CG == 1 ? 4 : 6);
+  static constexpr int SMEM_BYTES = BN == BN_SMALL ? 232448 - 1024 : STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmArgs {
@@ -48,6 +51,7 @@ struct GemmArgs {
   const bf16* resid; long long ldr;
   long long M, N, K;
   int m_blocks, n_blocks, group_m;
+  int a_rows, n_stages;  // small-M tile only: rows of A actually staged per k-block, ring depth
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
 
@@ -120,9 +124,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   static_assert(EPI != EVO_EPI_GELU_GATE || BN == BN_BIG, "the gate epilogue needs [l1 | l2] halves of a 256-column tile");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool SMALL = BN == BN_SMALL;
+  const int NST = SMALL ? g.n_stages : C_::STAGES;                    // ring depth
+  const int A_STRIDE = SMALL ? g.a_rows * BK * 2 : C_::A_BYTES;       // bytes of A per stage
+  const uint32_t STAGE_TX = (uint32_t)A_STRIDE + C_::B_BYTES;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + C_::STAGES * C_::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint8_t* smB = smem + (SMALL ? ((NST * A_STRIDE + (C_::A_BYTES - A_STRIDE) + 1023) & ~1023) : C_::STAGES * C_::A_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smB + NST * C_::B_BYTES);
   uint64_t* empty = full + C_::STAGES;
   uint64_t* tfull = empty + C_::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -163,8 +171,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if constexpr (CG == 1) {
-            mbar_arrive_expect_tx(&full[stage], C_::STAGE_BYTES);
-            tma_load_2d(smA + stage * C_::A_BYTES, &tmA, &full[stage], kb * BK, a_row);
+            mbar_arrive_expect_tx(&full[stage], STAGE_TX);
+            tma_load_2d(smA + stage * A_STRIDE, &tmA, &full[stage], kb * BK, a_row);
             tma_load_2d(smB + stage * C_::B_BYTES, &tmB, &full[stage], kb * BK, b_row);
           } else {
             // no remote arrive from the peer: a release.cluster arrive per stage costs more than the
@@ -174,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d_2sm(smA + stage * C_::A_BYTES, &tmA, bar, kb * BK, a_row);
             tma_load_2d_2sm(smB + stage * C_::B_BYTES, &tmB, bar, kb * BK, b_row);
           }
-          if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -191,13 +199,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t ad = umma_desc_k_sw128(smem_u32(smA + stage * C_::A_BYTES));
+          const uint64_t ad = umma_desc_k_sw128(smem_u32(smA + stage * A_STRIDE));
           const uint64_t bd = umma_desc_k_sw128(smem_u32(smB + stage * C_::B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k)   // +32 B per UMMA_K inside the 128B swizzle row
             umma_ss<CG>(d_tmem, ad + (uint64_t)(k * UK * 2 / 16), bd + (uint64_t)(k * UK * 2 / 16), idesc, (kb | k) != 0);
           if constexpr (CG == 1) umma_commit(&empty[stage]); else umma_commit_2sm(&empty[stage], 0b11);
-          if (++stage == C_::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         if constexpr (CG == 1) umma_commit(&tfull[acc]); else umma_commit_2sm(&tfull[acc], 0b11);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -249,11 +257,15 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   using C_ = Cfg<CG, BN>;
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda * 2, BK, BM, true))) return rc;
+  int a_rows = BM;
+  if (BN == BN_SMALL) { a_rows = 16; while (a_rows < BM && a_rows < p->M) a_rows *= 2; }
+  if ((rc = make_tmap_2d_bf16(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda * 2, BK, (uint32_t)a_rows, true))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmB, p->W, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->K * 2, BK, C_::B_ROWS, true))) return rc;
   GemmArgs g;
   g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K;
+  g.a_rows = a_rows;
+  g.n_stages = BN == BN_SMALL ? (a_rows <= 32 ? 16 : 8) : C_::STAGES;
   g.m_blocks = (int)((p->M + BM * CG - 1) / (BM * CG));
   g.n_blocks = (int)(p->N / BN);
   // Rasterisation: keep the smaller operand slab resident in L2 while the other one streams.

@@ -228,7 +228,7 @@ def test_hyena_full_size_properties():
 
 # ------------------------------------------------------------------ tensor-core linear layers
 @pytest.mark.parametrize("variant", [1, 0, 2])
-@pytest.mark.parametrize("M,N,K", [(1, 256, 64), (128, 256, 64), (300, 512, 256), (1000, 768, 256), (4096, 4096, 4096), (8200, 512, 1024)])
+@pytest.mark.parametrize("M,N,K", [(1, 256, 64), (16, 12288, 4096), (20, 768, 256), (40, 512, 4096), (128, 256, 64), (300, 512, 256), (1000, 768, 256), (4096, 4096, 4096), (8200, 512, 1024)])
 def test_gemm_all_epilogues(variant, M, N, K):
     if variant == 2 and M > 1000:
         pytest.skip("variant 2 is the small-M weight-streaming tile")
