@@ -328,11 +328,15 @@ extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t 
     a.seg_states = (float*)workspace; a.B = p->B; a.D = p->D; a.nseg = nseg; a.L = p->L; a.seg_len = seg_len;
     static bool attr_done = false;
     if (!attr_done) {
-      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES)));
+      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES)));
       attr_done = true;
     }
     dim3 grid(p->D / CH_PER_CTA, p->B, nseg), block(evo_hy2::THREADS);
+    // ring depth: one CTA per SM -> spend the shared memory on an 8-deep ring (absorbs HBM latency spikes of the
+    // strided 256-byte rows); more CTAs than SMs -> 4-deep so two CTAs co-reside and their warps hide each other's latency
+    a.nst = (long long)grid.x * grid.y * grid.z <= device_sm_count() ? 8 : 4;
+    const int SMEM_BYTES = smem_bytes(a.nst);
     if (p->state_only) {
       hyena_scan_tma_kernel<true><<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
       if ((rc = check_launch("hyena_scan_tma<state>"))) return rc;

@@ -20,12 +20,12 @@ using namespace evo;
 
 constexpr int NS = 8;
 constexpr int T2 = 16;                       // tokens per stage
-constexpr int STAGES = 4;
+constexpr int STAGES = 8;                    // maximum ring depth; the launch picks 4 (two CTAs per SM) or 8 (one)
 constexpr int CH_PER_CTA = 256;              // two heads of 128
 constexpr int SUB_BYTES = T2 * 128 * 2;      // one 128-column box
 constexpr int STAGE_BYTES = 6 * SUB_BYTES;   // [head0: x2 x1 v][head1: x2 x1 v]
 constexpr int THREADS = 160;                 // 4 compute warps + 1 producer warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 + 1024;
+constexpr int smem_bytes(int nst) { return nst * STAGE_BYTES + 128 + 1024; }
 
 struct Args2 {
   bf16* y;
@@ -35,7 +35,7 @@ struct Args2 {
   const bf16* halo; const float* state_in;
   float* state_out;
   float* seg_states;
-  int B, D, nseg;
+  int B, D, nseg, nst;
   long long L, seg_len;
 };
 
@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  const int NST = a.nst;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * STAGE_BYTES);
   uint64_t* empty = full + STAGES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,8 +83,8 @@ hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
     if (lane == 0) {
       tma_prefetch_desc(&tmZ);
       for (int k = 0; k < n_tiles; ++k) {
-        const int st = k % STAGES;
-        mbar_wait(&empty[st], ((uint32_t)(k / STAGES) & 1) ^ 1);
+        const int st = k % NST;
+        mbar_wait(&empty[st], ((uint32_t)(k / NST) & 1) ^ 1);
         uint8_t* dst = smem + st * STAGE_BYTES;
         const int row = (int)(t0 + (long long)k * T2);
         if (STATE_ONLY) {
@@ -248,8 +249,8 @@ hyena_scan_tma_kernel(const __grid_constant__ CUtensorMap tmZ, const Args2 a) {
   };
 
   for (int k = 0; k < n_tiles; ++k) {
-    const int st = k % STAGES;
-    mbar_wait(&full[st], (uint32_t)(k / STAGES) & 1);
+    const int st = k % NST;
+    mbar_wait(&full[st], (uint32_t)(k / NST) & 1);
     const uint32_t tile = smem_u32(smem) + st * STAGE_BYTES + hh * 3 * SUB_BYTES + j2 * 2;
     const int n_tok = (int)min((long long)T2, t1 - (t0 + (long long)k * T2));
     uint32_t* ytile = STATE_ONLY ? nullptr : yrow + (long long)k * T2 * ystride;
