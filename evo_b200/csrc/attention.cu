@@ -403,8 +403,10 @@ extern "C" int evo_attn_fwd_simple(const evo_attn_params* p, void* stream) {
   return check_launch("evo_attn_fwd_simple");
 }
 
+int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const evo_attn_params* p, cudaStream_t st);   // attention_pp.cu
+
 extern "C" size_t evo_attn_fwd_workspace(const evo_attn_params* p, int variant) {
-  if (variant == 1) return 0;
+  if (variant == 1 || variant == 2) return 0;
   long long lpad = (p->Lk + 7) / 8 * 8;
   return (size_t)p->B * p->H * HD * lpad * 2;
 }
@@ -430,8 +432,9 @@ extern "C" int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* work
     uint64_t str[3] = {(uint64_t)HD * 2, (uint64_t)p->kv_tok_stride * 2, (uint64_t)p->kv_batch_stride * 2};
     uint32_t box[4] = {64, 1, BKV, 1};
     if ((rc = make_tmap_4d(&tmK, p->k, dims, str, box))) return rc;
-    if (variant == 1) { if ((rc = make_tmap_4d(&tmV, p->v, dims, str, box))) return rc; }
+    if (variant == 1 || variant == 2) { if ((rc = make_tmap_4d(&tmV, p->v, dims, str, box))) return rc; }
   }
+  if (variant == 2) return evo_attn_pp_launch(tmQ, tmK, tmV, p, st);
   if (variant != 1) {
     long long lpad = (p->Lk + 7) / 8 * 8;
     size_t need = evo_attn_fwd_workspace(p, variant);

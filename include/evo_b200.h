@@ -138,7 +138,8 @@ typedef struct {
   float softmax_scale;
 } evo_attn_params;
 /* variant 0: V is transposed into the workspace first and consumed as a K-major operand;
- * variant 1: V is consumed in place as an MN-major operand (no workspace). */
+ * variant 1: V is consumed in place as an MN-major operand (no workspace);
+ * variant 2: ping-pong kernel: two query tiles per CTA, P kept in TMEM (A operand from TMEM), V in place. */
 size_t evo_attn_fwd_workspace(const evo_attn_params* p, int variant);
 int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* workspace, size_t workspace_bytes, void* stream);
 /* plain CUDA-core comparator for tests; never on the product path */

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 
-STAGES = ["elementwise", "hyena", "gemm1", "gemm2", "attn0", "attn1", "model", "perf_gemm", "perf_hyena", "perf_attn"]
+STAGES = ["elementwise", "hyena", "gemm1", "gemm2", "attn0", "attn1", "attn2", "model", "perf_gemm", "perf_hyena", "perf_attn"]
 
 
 def emit(stage, **kw):
@@ -373,7 +373,7 @@ def stage_perf_attn():
     for (B, L) in ((1, 8192), (8, 8193), (1, 32768)):
         qkv = torch.randn(B, L, 3, H, 128, device=dev).bfloat16()
         flops = 2.0 * B * L * L * H * 128       # causal-effective: 4*B*L^2*H*d / 2
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             ms = timeit(lambda: _attn(qkv, B, L, H, variant), iters=3, warm=1)
             emit("perf_attn", B=B, L=L, variant=variant, ms=ms, tflops=flops / ms / 1e9)
         if L <= 8193:
@@ -429,5 +429,5 @@ if __name__ == "__main__":
     else:
         _imports()
         {"elementwise": stage_elementwise, "hyena": stage_hyena, "gemm1": lambda: stage_gemm(1), "gemm2": lambda: stage_gemm(0),
-         "attn0": lambda: stage_attn(0), "attn1": lambda: stage_attn(1), "model": stage_model, "perf_gemm": stage_perf_gemm,
+         "attn0": lambda: stage_attn(0), "attn1": lambda: stage_attn(1), "attn2": lambda: stage_attn(2), "model": stage_model, "perf_gemm": stage_perf_gemm,
          "perf_hyena": stage_perf_hyena, "perf_attn": stage_perf_attn, "perf_decode": stage_perf_decode}[a.stage]()
