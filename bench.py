@@ -252,7 +252,7 @@ def bench_ours(args, wl):
         peaks = measured_peaks()
         by = {}
         for kind, work, a, b in prof:
-            d = by.setdefault(kind, [0.0, 0.0, 0])
+            d = by.setdefault(kind.split("/")[0], [0.0, 0.0, 0])
             d[0] += work; d[1] += a.elapsed_time(b); d[2] += 1
         roof = {}
         if "gemm" in by:

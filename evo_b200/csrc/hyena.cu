@@ -333,9 +333,9 @@ extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t 
       attr_done = true;
     }
     dim3 grid(p->D / CH_PER_CTA, p->B, nseg), block(evo_hy2::THREADS);
-    // ring depth: one CTA per SM -> spend the shared memory on an 8-deep ring (absorbs HBM latency spikes of the
-    // strided 256-byte rows); more CTAs than SMs -> 4-deep so two CTAs co-reside and their warps hide each other's latency
-    a.nst = (long long)grid.x * grid.y * grid.z <= device_sm_count() ? 8 : 4;
+    // ring depth 4 (96 KB): two CTAs can co-reside and hide each other's latency when the grid exceeds the SM count.
+    // An 8-deep ring for single-CTA-per-SM grids was measured and did not help (1.21 vs 1.06-1.13 ms at B=8, L=8193).
+    a.nst = 4;
     const int SMEM_BYTES = smem_bytes(a.nst);
     if (p->state_only) {
       hyena_scan_tma_kernel<true><<<grid, block, SMEM_BYTES, st>>>(tmZ, a);

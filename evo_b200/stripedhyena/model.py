@@ -233,7 +233,7 @@ class StripedHyena(nn.Module):
                        bias=bias.data_ptr() if bias is not None else None,
                        residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
                        M=M, N=N, K=K, epilogue=epi, variant=variant)
-        self._record("gemm", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
+        self._record(f"gemm/{N}x{K}/e{epi}/v{variant}", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
 
     def _rmsnorm(self, x, scale, out, rows):
         check(_lib.lib().evo_rmsnorm(ptr(x), ptr(scale), ptr(out), rows, self.config.hidden_size,

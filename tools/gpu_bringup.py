@@ -409,13 +409,22 @@ def stage_perf_decode():
         outs.append(s[:, 0])
         d["mha"].seqlen_offset += 1; d["hyena"].seqlen_offset += 1
     steady = sorted(times[8:])[len(times[8:]) // 2]
+    # per-kernel-class breakdown of one eager (non-graph) step with CUDA events
+    m._prof = []
+    s, d = m(ids[:, P + N - 1:P + N], inference_params_dict=d)
+    torch.cuda.synchronize()
+    agg = {}
+    for kind, work, e0, e1 in m._prof:
+        a_ = agg.setdefault(kind, [0, 0.0, 0.0]); a_[0] += 1; a_[1] += e0.elapsed_time(e1) * 1e3; a_[2] += work
+    m._prof = None
+    breakdown = {k: {"n": v[0], "us_total": round(v[1], 1), "us_each": round(v[1] / v[0], 1), "weight_GBs": round(v[2] / (2.0 * B) * 2 / (v[1] * 1e-6) / 1e9, 1)} for k, v in agg.items()}
     # sanity: teacher-forced decode logits vs one stateless forward over the same P+N tokens (last 8 positions)
     full, _ = m(ids[:2, :P + N])
     dec = torch.stack(outs, 1)[:2]
     e = (dec[:, -8:].float() - full[:, P + N - 8:].float()).abs()
     emit("perf_decode", B=B, prompt=P, steps=N, prefill_s=t_prefill, prefill_nt_s=B * P / t_prefill, first_step_ms=times[0] * 1e3, capture_step_ms=times[1] * 1e3,
          steady_ms_per_step=steady * 1e3, decode_nt_s=B / steady, decode_vs_stateless_max=e.max().item(), logit_scale=full.float().abs().max().item(),
-         weight_stream_floor_ms=12.9e9 / 6566.4e9 * 1e3)
+         weight_stream_floor_ms=12.9e9 / 6566.4e9 * 1e3, eager_breakdown=breakdown)
 
 
 if __name__ == "__main__":
