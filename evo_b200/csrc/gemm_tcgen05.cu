@@ -41,8 +41,12 @@ template <int CG, int BN> struct Cfg {
   // Small-M tile: A is staged COMPACT (only a_rows <= 128 rows per k-block; the MMA still reads a 128-row tile whose
   // remaining rows alias later stages / padding and only feed accumulator rows that are never stored), which leaves
   // room for a 16-deep ring of W tiles: bytes in flight, not tensor throughput, bound the weight-streaming GEMM.
-  static constexpr int STAGES = BN == BN_SMALL ? 16 : (CG == 1 ? 4 : 6);
-  static constexpr int SMEM_BYTES = BN == BN_SMALL ? 232448 - 1024 : STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // The weight-streaming kernel is bound by the serial wait -> 4 tiny MMAs -> commit round of its single issuing
+  // thread (~250 cycles per 8 KB k-block, measured 20-25 GB/s per CTA), not by bytes in flight: two CTAs per SM
+  // (<= 110 KB of shared memory each, 128 TMEM columns each) double the number of issuing threads.
+  static constexpr int STAGES = BN == BN_SMALL ? 8 : (CG == 1 ? 4 : 6);
+  static constexpr int SMEM_BYTES = BN == BN_SMALL ? 110 * 1024 : STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int CTAS_PER_SM = BN == BN_SMALL ? 2 : 1;
 };
 
 struct GemmArgs {
@@ -118,7 +122,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& g, long long row, in
 }
 
 template <int CG, int EPI, int BN>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, (BN == BN_SMALL ? 2 : 1))
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   using C_ = Cfg<CG, BN>;
   static_assert(EPI != EVO_EPI_GELU_GATE || BN == BN_BIG, "the gate epilogue needs [l1 | l2] halves of a 256-column tile");
@@ -265,7 +269,7 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.a_rows = a_rows;
-  g.n_stages = BN == BN_SMALL ? (a_rows <= 32 ? 16 : 8) : C_::STAGES;
+  g.n_stages = BN == BN_SMALL ? (a_rows <= 32 ? 8 : 4) : C_::STAGES;
   g.m_blocks = (int)((p->M + BM * CG - 1) / (BM * CG));
   g.n_blocks = (int)(p->N / BN);
   // Rasterisation: keep the smaller operand slab resident in L2 while the other one streams.
@@ -306,7 +310,7 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3(min(n_tiles, sms));
+    cfg.gridDim = dim3(min(n_tiles, sms * C_::CTAS_PER_SM));
   }
   EVO_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, g));
   return check_launch("evo_gemm");
