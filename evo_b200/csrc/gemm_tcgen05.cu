@@ -55,7 +55,7 @@ struct GemmArgs {
   const bf16* resid; long long ldr;
   long long M, N, K;
   int m_blocks, n_blocks, group_m;
-  int a_rows, n_stages;  // small-M tile only: rows of A actually staged per k-block, ring depth
+  int a_rows, n_stages, ksub;  // small-M tile only: rows of A staged per k-block, ring depth, 64-column k-blocks per ring stage
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
 
@@ -131,10 +131,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool SMALL = BN == BN_SMALL;
   const int NST = SMALL ? g.n_stages : C_::STAGES;                    // ring depth
   const int A_STRIDE = SMALL ? g.a_rows * BK * 2 : C_::A_BYTES;       // bytes of A per stage
-  const uint32_t STAGE_TX = (uint32_t)A_STRIDE + C_::B_BYTES;
+  const int KSUB = SMALL ? g.ksub : 1;                                // k-blocks per ring stage (one barrier round)
+  const uint32_t STAGE_TX = (uint32_t)KSUB * ((uint32_t)A_STRIDE + C_::B_BYTES);
   uint8_t* smA = smem;
-  uint8_t* smB = smem + (SMALL ? ((NST * A_STRIDE + (C_::A_BYTES - A_STRIDE) + 1023) & ~1023) : C_::STAGES * C_::A_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smB + NST * C_::B_BYTES);
+  uint8_t* smB = smem + (SMALL ? ((NST * KSUB * A_STRIDE + (C_::A_BYTES - A_STRIDE) + 1023) & ~1023) : C_::STAGES * C_::A_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smB + NST * KSUB * C_::B_BYTES);
   uint64_t* empty = full + C_::STAGES;
   uint64_t* tfull = empty + C_::STAGES;
   uint64_t* tempty = tfull + 2;
@@ -161,7 +162,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_tiles = g.m_blocks * g.n_blocks;           // m_blocks counts (BM*CG)-row blocks
   const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int nkb = (int)(g.K / BK);
+  const int nkb = (int)(g.K / (BK * KSUB));
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -176,8 +177,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty[stage], phase ^ 1);
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(&full[stage], STAGE_TX);
-            tma_load_2d(smA + stage * A_STRIDE, &tmA, &full[stage], kb * BK, a_row);
-            tma_load_2d(smB + stage * C_::B_BYTES, &tmB, &full[stage], kb * BK, b_row);
+            for (int u = 0; u < KSUB; ++u) {
+              tma_load_2d(smA + (stage * KSUB + u) * A_STRIDE, &tmA, &full[stage], (kb * KSUB + u) * BK, a_row);
+              tma_load_2d(smB + (stage * KSUB + u) * C_::B_BYTES, &tmB, &full[stage], (kb * KSUB + u) * BK, b_row);
+            }
           } else {
             // no remote arrive from the peer: a release.cluster arrive per stage costs more than the
             // 512-cycle k-block budget; the peer's bytes are already counted in the leader's expect_tx
@@ -203,11 +206,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t ad = umma_desc_k_sw128(smem_u32(smA + stage * A_STRIDE));
-          const uint64_t bd = umma_desc_k_sw128(smem_u32(smB + stage * C_::B_BYTES));
+          for (int u = 0; u < KSUB; ++u) {
+            const uint64_t ad = umma_desc_k_sw128(smem_u32(smA + (stage * KSUB + u) * A_STRIDE));
+            const uint64_t bd = umma_desc_k_sw128(smem_u32(smB + (stage * KSUB + u) * C_::B_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k)   // +32 B per UMMA_K inside the 128B swizzle row
-            umma_ss<CG>(d_tmem, ad + (uint64_t)(k * UK * 2 / 16), bd + (uint64_t)(k * UK * 2 / 16), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UK; ++k)   // +32 B per UMMA_K inside the 128B swizzle row
+              umma_ss<CG>(d_tmem, ad + (uint64_t)(k * UK * 2 / 16), bd + (uint64_t)(k * UK * 2 / 16), idesc, (kb | u | k) != 0);
+          }
           if constexpr (CG == 1) umma_commit(&empty[stage]); else umma_commit_2sm(&empty[stage], 0b11);
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
@@ -269,7 +274,9 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.a_rows = a_rows;
-  g.n_stages = BN == BN_SMALL ? (a_rows <= 32 ? 8 : 4) : C_::STAGES;
+  // small tile: two 64-column k-blocks per barrier round when K allows (halves the issue thread's serial rounds)
+  g.ksub = (BN == BN_SMALL && p->K % (2 * BK) == 0 && a_rows <= 32) ? 2 : 1;
+  g.n_stages = BN == BN_SMALL ? (a_rows <= 32 ? 8 / g.ksub : 4) : C_::STAGES;
   g.m_blocks = (int)((p->M + BM * CG - 1) / (BM * CG));
   g.n_blocks = (int)(p->N / BN);
   // Rasterisation: keep the smaller operand slab resident in L2 while the other one streams.
