@@ -36,6 +36,11 @@ elif what == "hyena":
     z = torch.randn(B, L, 3 * D, device=dev).bfloat16()
     for _ in range(3):
         G._hyena_call(z, f, B, L, D, H, want_state=False)
+elif what == "attn2":
+    B, L, H = 2, 8193, 32
+    qkv = torch.randn(B, L, 3, H, 128, device=dev).bfloat16()
+    for _ in range(3):
+        G._attn(qkv, B, L, H, 2)
 elif what == "attn":
     B, L, H = 2, 8193, 32
     qkv = torch.randn(B, L, 3, H, 128, device=dev).bfloat16()
