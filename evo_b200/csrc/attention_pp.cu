@@ -177,21 +177,28 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         const long long key0 = (long long)j * BKV;
         const bool need_mask = key0 + BKV - 1 > pos;
-        // ---- pass 1: row max (TMEM reads are cheap; holding 128 scores would cost 128 registers)
-        float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int c = 0; c < BKV; c += 64) {
-          uint32_t t0[32], t1[32];
-          tmem_ld_32x32(s_addr + c, t0); tmem_ld_32x32(s_addr + c + 32, t1);
+        // ---- one TMEM read of the row (tcgen05.ld moves ~64 B/clk: a second pass over S costs as much as the MMAs)
+        float sc[BKV];
+        {
+          uint32_t t0[32], t1[32], t2[32], t3[32];
+          tmem_ld_32x32(s_addr, t0); tmem_ld_32x32(s_addr + 32, t1); tmem_ld_32x32(s_addr + 64, t2); tmem_ld_32x32(s_addr + 96, t3);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float v0 = __uint_as_float(t0[i]), v1 = __uint_as_float(t1[i]);
-            if (need_mask) { if (key0 + c + i > pos) v0 = -INFINITY; if (key0 + c + 32 + i > pos) v1 = -INFINITY; }
-            mxs[i & 1] = fmaxf(mxs[i & 1], v0); mxs[2 + (i & 1)] = fmaxf(mxs[2 + (i & 1)], v1);
+            sc[i] = __uint_as_float(t0[i]); sc[32 + i] = __uint_as_float(t1[i]);
+            sc[64 + i] = __uint_as_float(t2[i]); sc[96 + i] = __uint_as_float(t3[i]);
           }
         }
-        float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])) * a.scale_log2;
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i) if (key0 + i > pos) sc[i] = -INFINITY;
+        }
+        float mxs[8];
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) mxs[q8] = sc[q8];
+#pragma unroll
+        for (int i = 8; i < BKV; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], sc[i]);
+        float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])), fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]))) * a.scale_log2;
         float alpha = 1.f;
         bool grow = mx > m_ref + 8.f;
         if (j == 0) { m_ref = (mx == -INFINITY) ? 0.f : mx; grow = false; }
@@ -208,23 +215,21 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tmem_st_32x32(o_addr + c, tt);
           }
         }
-        // ---- pass 2: P = exp2(s*scale - m_ref) as bf16, written over the S columns already consumed
-        float ls0 = 0.f, ls1 = 0.f;
+        // ---- P = exp2(s*scale - m_ref) as bf16, written over the S columns (all of S is in registers by now)
+        float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll
         for (int c = 0; c < BKV; c += 32) {
-          uint32_t tt[32], w[16];
-          tmem_ld_32x32(s_addr + c, tt);
-          tmem_ld_wait();
+          uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float v0 = __uint_as_float(tt[2 * i]), v1 = __uint_as_float(tt[2 * i + 1]);
-            if (need_mask) { if (key0 + c + 2 * i > pos) v0 = -INFINITY; if (key0 + c + 2 * i + 1 > pos) v1 = -INFINITY; }
-            const float p0 = ex2(fmaf(v0, a.scale_log2, -m_ref)), p1 = ex2(fmaf(v1, a.scale_log2, -m_ref));
-            ls0 += p0; ls1 += p1;
+            const float p0 = ex2(fmaf(sc[c + 2 * i], a.scale_log2, -m_ref)), p1 = ex2(fmaf(sc[c + 2 * i + 1], a.scale_log2, -m_ref));
+            if (i & 1) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
             w[i] = pack_bf16(p0, p1);
           }
-          tmem_st_32x32_x16(s_addr + c / 2, w);       // P columns [c/2, c/2+16) alias S columns < c+32: already read
+          tmem_st_32x32_x16(s_addr + c / 2, w);
         }
+        const float ls0_ = ls0 + ls2, ls1_ = ls1 + ls3;
+        ls0 = ls0_; ls1 = ls1_;
         l += ls0 + ls1;
         tmem_st_wait();
         tc_fence_before();
