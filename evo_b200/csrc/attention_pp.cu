@@ -38,6 +38,23 @@ struct Args {
 
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// 2^x for two values on the FMA pipe (the MUFU pipe, 16 ex2/clk/SM, is the co-bottleneck of this kernel):
+// round-to-nearest split x = n + f via the 1.5*2^23 trick, degree-3 minimax of 2^f on [-0.5, 0.5]
+// (max relative error 7.7e-5, far below the bf16 rounding P gets anyway), exponent patched in with integer adds.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, nmagic);
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.05508868f, 0.05508868f), make_float2(0.24260405f, 0.24260405f));
+  p = __ffma2_rn(p, f, make_float2(0.69327624f, 0.69327624f));
+  p = __ffma2_rn(p, f, make_float2(0.99992894f, 0.99992894f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -222,7 +239,14 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2(fmaf(sc[c + 2 * i], a.scale_log2, -m_ref)), p1 = ex2(fmaf(sc[c + 2 * i + 1], a.scale_log2, -m_ref));
+            float p0, p1;
+            if ((c >> 5) & 1) {       // odd 32-column chunks: FMA-pipe polynomial; even chunks: MUFU
+              const float2 xx = __ffma2_rn(make_float2(sc[c + 2 * i], sc[c + 2 * i + 1]), make_float2(a.scale_log2, a.scale_log2), make_float2(-m_ref, -m_ref));
+              const float2 pp = exp2_poly2(xx);
+              p0 = pp.x; p1 = pp.y;
+            } else {
+              p0 = ex2(fmaf(sc[c + 2 * i], a.scale_log2, -m_ref)); p1 = ex2(fmaf(sc[c + 2 * i + 1], a.scale_log2, -m_ref));
+            }
             if (i & 1) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
             w[i] = pack_bf16(p0, p1);
           }
