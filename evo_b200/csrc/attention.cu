@@ -430,7 +430,7 @@ extern "C" int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* work
   {
     uint64_t dims[4] = {(uint64_t)HD, (uint64_t)p->H, (uint64_t)p->Lk, (uint64_t)p->B};
     uint64_t str[3] = {(uint64_t)HD * 2, (uint64_t)p->kv_tok_stride * 2, (uint64_t)p->kv_batch_stride * 2};
-    uint32_t box[4] = {64, 1, (uint32_t)(variant == 2 ? 64 : BKV), 1};      // the ping-pong kernel walks 64-key tiles
+    uint32_t box[4] = {64, 1, BKV, 1};
     if ((rc = make_tmap_4d(&tmK, p->k, dims, str, box))) return rc;
     if (variant == 1 || variant == 2) { if ((rc = make_tmap_4d(&tmV, p->v, dims, str, box))) return rc; }
   }
