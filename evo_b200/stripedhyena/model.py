@@ -33,7 +33,8 @@ from .cache import InferenceParams, RecurrentInferenceParams
 # sustains ~2 % more (profiles/r01_bench_8k_variants_call5.json, same box back to back)
 GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "1"))
 GEMM_VARIANT_GATE = int(os.environ.get("EVO_B200_GEMM_VARIANT_GATE", "1"))
-ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "1"))
+# attention: 2 = ping-pong kernel (two query tiles per CTA, P in TMEM): 0.89-1.07 PFLOP/s vs 0.86-1.07 for variant 1
+ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "2"))
 
 
 def _round_up(x: int, m: int) -> int:
