@@ -55,6 +55,7 @@ struct GemmArgs {
   const bf16* resid; long long ldr;
   long long M, N, K;
   int m_blocks, n_blocks, group_m;
+  int b_tiled;           // small-M tile only: W is tile-major [N/64][K/64][64][64] (contiguous 8 KB tiles: every DRAM page opened is fully used)
   int a_rows, n_stages, ksub;  // small-M tile only: rows of A staged per k-block, ring depth, 64-column k-blocks per ring stage
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
@@ -179,7 +180,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_arrive_expect_tx(&full[stage], STAGE_TX);
             for (int u = 0; u < KSUB; ++u) {
               tma_load_2d(smA + (stage * KSUB + u) * A_STRIDE, &tmA, &full[stage], (kb * KSUB + u) * BK, a_row);
-              tma_load_2d(smB + (stage * KSUB + u) * C_::B_BYTES, &tmB, &full[stage], (kb * KSUB + u) * BK, b_row);
+              if (SMALL && g.b_tiled) tma_load_4d(smB + (stage * KSUB + u) * C_::B_BYTES, &tmB, &full[stage], 0, 0, kb * KSUB + u, n_blk);
+              else tma_load_2d(smB + (stage * KSUB + u) * C_::B_BYTES, &tmB, &full[stage], (kb * KSUB + u) * BK, b_row);
             }
           } else {
             // no remote arrive from the peer: a release.cluster arrive per stage costs more than the
@@ -269,11 +271,18 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   int a_rows = BM;
   if (BN == BN_SMALL) { a_rows = 16; while (a_rows < BM && a_rows < p->M) a_rows *= 2; }
   if ((rc = make_tmap_2d_bf16(&tmA, p->A, (uint64_t)p->K, (uint64_t)p->M, (uint64_t)p->lda * 2, BK, (uint32_t)a_rows, true))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmB, p->W, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->K * 2, BK, C_::B_ROWS, true))) return rc;
+  const bool b_tiled = BN == BN_SMALL && p->variant == 3;
+  if (b_tiled) {
+    uint64_t dims[4] = {(uint64_t)BK, (uint64_t)BN, (uint64_t)(p->K / BK), (uint64_t)(p->N / BN)};
+    uint64_t str[3] = {(uint64_t)BK * 2, (uint64_t)BK * BN * 2, (uint64_t)(p->K / BK) * BK * BN * 2};
+    uint32_t box[4] = {(uint32_t)BK, (uint32_t)BN, 1, 1};
+    if ((rc = make_tmap_nd_bf16(&tmB, p->W, 4, dims, str, box, true))) return rc;
+  } else if ((rc = make_tmap_2d_bf16(&tmB, p->W, (uint64_t)p->K, (uint64_t)p->N, (uint64_t)p->K * 2, BK, C_::B_ROWS, true))) return rc;
   GemmArgs g;
   g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.a_rows = a_rows;
+  g.b_tiled = b_tiled;
   // small tile: two 64-column k-blocks per barrier round when K allows (halves the issue thread's serial rounds)
   g.ksub = (BN == BN_SMALL && p->K % (2 * BK) == 0 && a_rows <= 32) ? 2 : 1;
   g.n_stages = BN == BN_SMALL ? (a_rows <= 32 ? 8 / g.ksub : 4) : C_::STAGES;
@@ -350,7 +359,7 @@ extern "C" int evo_gemm(const evo_gemm_params* p, void* stream) {
   if (p->epilogue == EVO_EPI_RESID || p->epilogue == EVO_EPI_BIAS_RESID)
     EVO_REQUIRE(p->residual != nullptr && p->ldr % 8 == 0 && ((uintptr_t)p->residual % 16) == 0, "evo_gemm: residual epilogue without a valid residual");
   if (p->M == 0) return 0;
-  if (p->variant == 2) return dispatch_epi<1, BN_SMALL>(p, (cudaStream_t)stream);
+  if (p->variant == 2 || p->variant == 3) return dispatch_epi<1, BN_SMALL>(p, (cudaStream_t)stream);
   if (p->variant == 1) return dispatch_epi<1, BN_BIG>(p, (cudaStream_t)stream);
   return dispatch_epi<2, BN_BIG>(p, (cudaStream_t)stream);
 }

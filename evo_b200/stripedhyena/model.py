@@ -150,6 +150,8 @@ class StripedHyena(nn.Module):
         self.gemm_variant_gate = GEMM_VARIANT_GATE
         self.attn_variant = ATTN_VARIANT
         self.decode_graph = os.environ.get("EVO_B200_DECODE_GRAPH", "1") != "0"
+        self.decode_tiled = os.environ.get("EVO_B200_DECODE_TILED", "1") != "0"
+        self._tiled = None   # tile-major weight copies for the weight-streaming decode GEMMs
         self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
         self._prof = None   # set to a list to record (kind, algorithmic work, start event, end event) per kernel call
 
@@ -173,6 +175,7 @@ class StripedHyena(nn.Module):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._packed = None
         self._decode = None
+        self._tiled = None
         return out
 
     def _apply(self, fn, *a, **kw):
@@ -180,6 +183,7 @@ class StripedHyena(nn.Module):
         self._packed = None
         self._rope = None
         self._decode = None
+        self._tiled = None
         return out
 
     # ---- weight packing (once per load / move) ---------------------------------------------
@@ -402,6 +406,30 @@ class StripedHyena(nn.Module):
                 return False
         return True
 
+    @staticmethod
+    def _tile64(w):
+        """(N, K) row-major -> (N/64, K/64, 64, 64): each 64x64 tile is one contiguous 8 KB block, so the decode GEMM's TMA
+        boxes use every DRAM page they open (row-major tiles touch 64 pages for 128 bytes each: measured 2.2-3.5 TB/s)."""
+        n, k = w.shape
+        return w.view(n // 64, 64, k // 64, 64).permute(0, 2, 1, 3).contiguous()
+
+    def _ensure_tiled(self):
+        if self._tiled is not None:
+            return self._tiled
+        t = {}
+        with torch.no_grad():
+            for i, blk in enumerate(self.blocks):
+                pk = self._packed[i]
+                e = {"w12": self._tile64(pk["w12"]), "w3": self._tile64(pk["w3"])}
+                if i in self._attn_idxs:
+                    e["in"], e["out"] = self._tile64(blk.inner_mha_cls.Wqkv.weight.data), self._tile64(blk.inner_mha_cls.out_proj.weight.data)
+                else:
+                    e["in"], e["out"] = self._tile64(blk.projections.weight.data), self._tile64(blk.out_filter_dense.weight.data)
+                t[i] = e
+            t["unembed"] = self._tile64(self.unembed.weight.data)
+        self._tiled = t
+        return t
+
     def _decode_body(self, x, pos_dev, ipd, B):
         """One token per sequence through all blocks; every launch reads the position from pos_dev."""
         cfg = self.config
@@ -410,7 +438,9 @@ class StripedHyena(nn.Module):
         dev = x.device
         lib = _lib.lib()
         mha_ip, hy_ip = ipd["mha"], ipd["hyena"]
-        G2 = 2  # weight-streaming tile variant
+        tiled = self._ensure_tiled() if self.decode_tiled else None
+        G2 = 3 if tiled is not None else 2       # weight-streaming tiles (3: tile-major weights)
+        wsel = (lambda i, name, w: tiled[i][name]) if tiled is not None else (lambda i, name, w: w)
         u = torch.empty(B, d, dtype=torch.bfloat16, device=dev)
         check(lib.evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u), B, d, V, self._stream()), "evo_embed")
         nsplit = max(1, min(16, -(-2 * torch.cuda.get_device_properties(dev).multi_processor_count // (H * B))))
@@ -421,7 +451,7 @@ class StripedHyena(nn.Module):
             if i in self._attn_idxs:
                 mha = blk.inner_mha_cls
                 qkv = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
-                self._gemm(xn, mha.Wqkv.weight, qkv, B, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias, variant=G2)
+                self._gemm(xn, wsel(i, "in", mha.Wqkv.weight), qkv, B, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias, variant=G2)
                 cache = mha_ip.key_value_memory_dict[i]
                 cos, sin = self._rope_tables(cache.shape[1], dev)
                 check(lib.evo_decode_qkv_prep(ptr(qkv), ptr(cache), ptr(cos), ptr(sin), ptr(pos_dev), B, H, hd, cache.shape[1], self._stream()), "evo_decode_qkv_prep")
@@ -430,32 +460,32 @@ class StripedHyena(nn.Module):
                 ctx = xn
                 check(lib.evo_decode_attn(ptr(qkv), ptr(cache), ptr(ctx), ptr(pos_dev), B, H, hd, cache.shape[1], nsplit,
                                           1.0 / math.sqrt(hd), ptr(ws), nws, self._stream()), "evo_decode_attn")
-                self._gemm(ctx, mha.out_proj.weight, u2, B, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID,
+                self._gemm(ctx, wsel(i, "out", mha.out_proj.weight), u2, B, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID,
                            bias=mha.out_proj.bias, resid=u, variant=G2)
             else:
                 f = blk.filter
                 z = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
-                self._gemm(xn, blk.projections.weight, z, B, 3 * d, d, EPI_BIAS, bias=blk.projections.bias, variant=G2)
+                self._gemm(xn, wsel(i, "in", blk.projections.weight), z, B, 3 * d, d, EPI_BIAS, bias=blk.projections.bias, variant=G2)
                 y = xn
                 check(lib.evo_hyena_step(ptr(z), ptr(y), ptr(hy_ip.fir_state_dict[i]), ptr(torch.view_as_real(hy_ip.state_dict[i])),
                                          ptr(f.short_filter_weight), ptr(f.short_filter_bias), ptr(f.D), ptr(f.poles), ptr(f.residues),
                                          B, d, cfg.state_size, H, self._stream()), "evo_hyena_step")
-                self._gemm(y, blk.out_filter_dense.weight, u2, B, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u, variant=G2)
+                self._gemm(y, wsel(i, "out", blk.out_filter_dense.weight), u2, B, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u, variant=G2)
             pk = self._packed[i]
             xn2 = xn
             self._rmsnorm(u2, blk.post_norm.scale, xn2, B)
             t = torch.empty(B, 2 * pk["ipad"], dtype=torch.bfloat16, device=dev)
-            self._gemm(xn2, pk["w12"], t, B, 2 * pk["ipad"], d, EPI_NONE, variant=G2)
+            self._gemm(xn2, wsel(i, "w12", pk["w12"]), t, B, 2 * pk["ipad"], d, EPI_NONE, variant=G2)
             g = torch.empty(B, pk["ipad"], dtype=torch.bfloat16, device=dev)
             check(lib.evo_gelu_gate_interleaved(ptr(t), ptr(g), B, pk["ipad"], self._stream()), "evo_gelu_gate_interleaved")
             u = torch.empty_like(u2)
-            self._gemm(g, pk["w3"], u, B, d, pk["ipad"], EPI_RESID, resid=u2, variant=G2)
+            self._gemm(g, wsel(i, "w3", pk["w3"]), u, B, d, pk["ipad"], EPI_RESID, resid=u2, variant=G2)
         if self.norm is not None:
             xn = torch.empty_like(u)
             self._rmsnorm(u, self.norm.scale, xn, B)
             u = xn
         logits = torch.empty(B, V, dtype=torch.bfloat16, device=dev)
-        self._gemm(u, self.unembed.weight, logits, B, V, d, EPI_NONE, variant=G2)
+        self._gemm(u, tiled["unembed"] if tiled is not None else self.unembed.weight, logits, B, V, d, EPI_NONE, variant=G2)
         return logits
 
     def _decode_forward(self, x, ipd):

@@ -62,7 +62,8 @@ typedef struct {
   const void* residual; int64_t ldr;
   int64_t M, N, K;
   int epilogue;
-  int variant;                   /* 0 = 2-CTA 256x256 tiles; 1 = 1-CTA 128x256 tiles; 2 = 1-CTA 128x64 weight-streaming tiles (small M) */
+  int variant;                   /* 0 = 2-CTA 256x256 tiles; 1 = 1-CTA 128x256 tiles; 2 = 1-CTA 128x64 weight-streaming tiles (small M);
+                                    3 = like 2 with W given tile-major: (N/64, K/64, 64, 64), i.e. W.view(N/64,64,K/64,64).permute(0,2,1,3) */
 } evo_gemm_params;
 int evo_gemm(const evo_gemm_params* p, void* stream);
 /* test comparator only (cuBLASLt, plain C = A.W^T [+bias]); never on the product path */

@@ -266,6 +266,19 @@ def test_gemm_all_epilogues(variant, M, N, K):
     assert (out == ref).float().mean() > (0.97 if K <= 1024 else 0.88)
 
 
+def test_gemm_tile_major_weights_variant3():
+    """variant 3 = variant 2 reading W tile-major; must give exactly the same bits as variant 2."""
+    torch.manual_seed(0)
+    for (M, N, K) in ((16, 12288, 4096), (5, 512, 256), (16, 4096, 11008)):
+        a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+        w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=DEV).bfloat16()
+        wt = StripedHyena._tile64(w)
+        ref = G._gemm(a, w, M, N, K, _lib.EPI_BIAS, 2, bias=bias)
+        out = G._gemm(a, wt, M, N, K, _lib.EPI_BIAS, 3, bias=bias)
+        assert torch.equal(out, ref)
+
+
 def test_gemm_rejects_bad_shapes():
     a = torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV)
     w = torch.zeros(100, 64, dtype=torch.bfloat16, device=DEV)

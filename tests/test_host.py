@@ -167,3 +167,42 @@ def test_generation_prompt_forcing_bookkeeping():
     assert model.calls[0] == ((1, 3), 0)
     assert model.calls[1] == ((1, 1), 8)          # jump to len(prompt), not 3
     assert len(model.calls) == 5 + 3
+
+
+def test_load_checkpoint_from_local_safetensors(tmp_path):
+    """Checkpoint ingest (evo/models.py:96-150 contract): sharded safetensors with the HF 'backbone.' prefix and NO
+    'unembed.weight' (tied embeddings) -> strict load -> bf16 except poles/residues; config from a YAML with the
+    reference's keys."""
+    import json
+    import yaml
+    from safetensors.torch import save_file
+    from evo_b200.models import load_checkpoint
+
+    cfg = O.tiny_config(num_layers=3, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=9)
+    sd.pop("unembed.weight")
+    names = sorted(sd)
+    shards = {"model-00001-of-00002.safetensors": names[: len(names) // 2], "model-00002-of-00002.safetensors": names[len(names) // 2:]}
+    weight_map = {}
+    for fname, keys in shards.items():
+        save_file({"backbone." + k: sd[k].contiguous() for k in keys}, str(tmp_path / fname))
+        weight_map.update({"backbone." + k: fname for k in keys})
+    (tmp_path / "model.safetensors.index.json").write_text(json.dumps({"weight_map": weight_map}))
+    cfg_path = tmp_path / "tiny.yml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    m = load_checkpoint("evo-1-8k-base", config_path=str(cfg_path), model_dir=str(tmp_path))
+    got = m.state_dict()
+    assert set(got) == set(O.state_dict_spec(cfg))
+    for k in names:
+        want = sd[k] if ("poles" in k or "residues" in k) else sd[k].to(torch.bfloat16)
+        assert torch.equal(got[k].cpu(), want), k
+    assert torch.equal(got["unembed.weight"], got["embedding_layer.weight"])
+    assert got["blocks.0.filter.poles"].dtype == torch.float32 and got["blocks.0.mlp.l1.weight"].dtype == torch.bfloat16
+    # a checkpoint with a missing tensor must fail loudly (strict=True)
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    save_file({"backbone." + k: sd[k].contiguous() for k in names[1:]}, str(bad / "model.safetensors"))
+    with pytest.raises(RuntimeError):
+        load_checkpoint("evo-1-8k-base", config_path=str(cfg_path), model_dir=str(bad))
+    with pytest.raises(FileNotFoundError):
+        load_checkpoint("evo-1-8k-base", config_path=str(cfg_path), model_dir=str(tmp_path / "nope"))
