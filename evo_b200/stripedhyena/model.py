@@ -150,7 +150,9 @@ class StripedHyena(nn.Module):
         self.gemm_variant_gate = GEMM_VARIANT_GATE
         self.attn_variant = ATTN_VARIANT
         self.decode_graph = os.environ.get("EVO_B200_DECODE_GRAPH", "1") != "0"
-        self.decode_tiled = os.environ.get("EVO_B200_DECODE_TILED", "1") != "0"
+        # tile-major weight copies for decode (GEMM variant 3): validated bit-identical but no faster on B200 (6.57 vs 6.65 ms/step:
+        # the small-M GEMM is bound by bytes in flight per CTA and by too few CTAs at N=4096, not by DRAM page locality), so off
+        self.decode_tiled = os.environ.get("EVO_B200_DECODE_TILED", "0") != "0"
         self._tiled = None   # tile-major weight copies for the weight-streaming decode GEMMs
         self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
         self._prof = None   # set to a list to record (kind, algorithmic work, start event, end event) per kernel call
