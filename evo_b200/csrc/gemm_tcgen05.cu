@@ -156,7 +156,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator buffers (power of two >= 32)
   if (warp == 2) { tmem_alloc<CG>(tmem_slot, TMEM_COLS); tmem_relinquish<CG>(); }
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (CG == 2) { cluster_sync_all(); __syncthreads(); }   // (the CTA barrier only makes the hand-off visible to racecheck)
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
