@@ -23,6 +23,13 @@ class GemmParams(C.Structure):
                 ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("epilogue", C.c_int), ("variant", C.c_int)]
 
 
+class GemmSmallMParams(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int64),
+                ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("epilogue", C.c_int),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 class HyenaParams(C.Structure):
     _fields_ = [("z", C.c_void_p), ("y", C.c_void_p), ("fir_w", C.c_void_p), ("fir_b", C.c_void_p), ("Dskip", C.c_void_p),
                 ("poles", C.c_void_p), ("residues", C.c_void_p),
@@ -48,6 +55,10 @@ SIGNATURES = {
     "evo_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "evo_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
     "evo_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "evo_gemm_smallm_workspace": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "evo_gemm_smallm": (C.c_int, [C.POINTER(GemmSmallMParams), C.c_void_p]),
+    "evo_set_pdl": (C.c_int, [C.c_int]),
+    "evo_debug_smallm_trace": (None, [C.c_void_p]),
     "evo_gemm_cublaslt_reference": (C.c_int, [C.POINTER(GemmParams), C.c_void_p, C.c_size_t, C.c_void_p]),
     "evo_hyena_fwd_workspace": (C.c_size_t, [C.POINTER(HyenaParams)]),
     "evo_hyena_fwd": (C.c_int, [C.POINTER(HyenaParams), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libevo_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "hyena.cu", "gemm_tcgen05.cu", "attention.cu", "attention_pp.cu", "gemm_cublaslt_ref.cu", "decode.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "hyena.cu", "gemm_tcgen05.cu", "gemm_smallm.cu", "attention.cu", "attention_pp.cu", "gemm_cublaslt_ref.cu", "decode.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]

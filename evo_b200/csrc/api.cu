@@ -9,6 +9,8 @@ namespace evo {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_pdl{0};
+int pdl_level() { return g_pdl.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -90,4 +92,5 @@ const char* evo_last_error(void) { return evo::g_err; }
 int evo_abi_version(void) { return 1; }
 int64_t evo_launch_count(void) { return evo::g_launches.load(); }
 void evo_reset_launch_count(void) { evo::g_launches.store(0); }
+int evo_set_pdl(int level) { return evo::g_pdl.exchange(level < 0 ? 0 : (level > 2 ? 2 : level)); }
 }

@@ -31,6 +31,7 @@ __global__ void gelu_gate_kernel(const bf16* __restrict__ t, bf16* __restrict__ 
 // qkv (B, 3, H, 128) in place; cos/sin tables indexed by absolute position.
 __global__ void decode_qkv_prep_kernel(bf16* __restrict__ qkv, bf16* __restrict__ cache, const bf16* __restrict__ cos, const bf16* __restrict__ sin,
                                        const long long* __restrict__ pos_ptr, int B, int H, long long max_seqlen) {
+  pdl_launch_dependents(); pdl_wait();
   const long long pos = *pos_ptr;
   int idx = blockIdx.x * blockDim.x + threadIdx.x;       // (b, h, i) i in [0, 64)
   if (idx >= B * H * 64 || pos >= max_seqlen) return;
@@ -59,6 +60,7 @@ constexpr int DT = 128;
 __global__ void __launch_bounds__(DT) decode_attn_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ cache, float* __restrict__ part_o,
                                                          float* __restrict__ part_ml, const long long* __restrict__ pos_ptr,
                                                          int H, long long max_seqlen, int nsplit, float scale) {
+  pdl_launch_dependents(); pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x;
   const long long nk = min(*pos_ptr + 1, max_seqlen);
   const long long per = (nk + nsplit - 1) / nsplit;
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(DT) decode_attn_kernel(const bf16* __restrict_
 
 __global__ void decode_attn_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, bf16* __restrict__ out,
                                          int H, int nsplit) {
+  pdl_launch_dependents(); pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   const long long base = ((long long)b * H + h) * nsplit;
   float M = -INFINITY;
@@ -157,8 +160,8 @@ extern "C" int evo_decode_qkv_prep(void* qkv, void* cache, const void* cos, cons
                                    int B, int H, int hd, int64_t max_seqlen, void* stream) {
   EVO_REQUIRE(hd == HD, "evo_decode_qkv_prep: head_dim %d unsupported", hd);
   int n = B * H * 64;
-  decode_qkv_prep_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((bf16*)qkv, (bf16*)cache, (const bf16*)cos, (const bf16*)sin,
-                                                                           (const long long*)pos, B, H, max_seqlen);
+  EVO_CUDA(launch_pdl(decode_qkv_prep_kernel, dim3((n + 127) / 128), dim3(128), 0, (cudaStream_t)stream, (bf16*)qkv, (bf16*)cache, (const bf16*)cos, (const bf16*)sin,
+                      (const long long*)pos, B, H, max_seqlen));
   return check_launch("evo_decode_qkv_prep");
 }
 
@@ -171,11 +174,11 @@ extern "C" int evo_decode_attn(const void* qkv, const void* cache, void* out, co
   EVO_REQUIRE(workspace && workspace_bytes >= evo_decode_attn_workspace(B, H, nsplit), "evo_decode_attn: workspace too small");
   float* part_o = (float*)workspace;
   float* part_ml = part_o + (size_t)B * H * nsplit * HD;
-  decode_attn_kernel<<<dim3(H, B, nsplit), DT, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const bf16*)cache, part_o, part_ml,
-                                                                         (const long long*)pos, H, max_seqlen, nsplit, softmax_scale);
+  EVO_CUDA(launch_pdl(decode_attn_kernel, dim3(H, B, nsplit), dim3(DT), 0, (cudaStream_t)stream, (const bf16*)qkv, (const bf16*)cache, part_o, part_ml,
+                      (const long long*)pos, H, max_seqlen, nsplit, softmax_scale));
   int rc = check_launch("evo_decode_attn");
   if (rc) return rc;
-  decode_attn_merge_kernel<<<dim3(H, B), HD, 0, (cudaStream_t)stream>>>(part_o, part_ml, (bf16*)out, H, nsplit);
+  EVO_CUDA(launch_pdl(decode_attn_merge_kernel, dim3(H, B), dim3(HD), 0, (cudaStream_t)stream, (const float*)part_o, (const float*)part_ml, (bf16*)out, H, nsplit));
   return check_launch("evo_decode_attn_merge");
 }
 

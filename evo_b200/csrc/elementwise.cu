@@ -10,6 +10,7 @@ using namespace evo;
 template <typename IdT>
 __global__ void embed_kernel(const IdT* __restrict__ ids, const uint4* __restrict__ table, uint4* __restrict__ out,
                              int64_t n_tokens, int row_vec, int vocab) {
+  pdl_launch_dependents(); pdl_wait();
   int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (warp >= n_tokens) return;
   long long id = (long long)ids[warp];
@@ -26,9 +27,9 @@ extern "C" int evo_embed(const void* ids, int ids_are_i64, const void* table, vo
   int wpb = 8;
   dim3 grid((unsigned)((n_tokens + wpb - 1) / wpb)), block(wpb * 32);
   if (ids_are_i64)
-    embed_kernel<long long><<<grid, block, 0, (cudaStream_t)stream>>>((const long long*)ids, (const uint4*)table, (uint4*)out, n_tokens, D / 8, vocab);
+    EVO_CUDA(launch_pdl(embed_kernel<long long>, grid, block, 0, (cudaStream_t)stream, (const long long*)ids, (const uint4*)table, (uint4*)out, n_tokens, D / 8, vocab));
   else
-    embed_kernel<int><<<grid, block, 0, (cudaStream_t)stream>>>((const int*)ids, (const uint4*)table, (uint4*)out, n_tokens, D / 8, vocab);
+    EVO_CUDA(launch_pdl(embed_kernel<int>, grid, block, 0, (cudaStream_t)stream, (const int*)ids, (const uint4*)table, (uint4*)out, n_tokens, D / 8, vocab));
   return check_launch("evo_embed");
 }
 
@@ -40,6 +41,7 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ scale,
                                                       uint4* __restrict__ out, int64_t rows, int nvec_per_lane,
                                                       float inv_sqrt_d, float eps) {
+  pdl_launch_dependents(); pdl_wait();
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
@@ -80,16 +82,73 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ 
   }
 }
 
+// Few rows (decode step): one 256-thread CTA per row instead of one warp per row -- the row and the scale are fetched
+// by 8 warps at once (the warp-per-row kernel is a 5 us latency chain on 2 CTAs at 16 rows).  Same rounding chain.
+__global__ void __launch_bounds__(256) rmsnorm_row_kernel(const uint4* __restrict__ x, const uint4* __restrict__ scale,
+                                                          uint4* __restrict__ out, int row_vec, float inv_sqrt_d, float eps) {
+  pdl_launch_dependents(); pdl_wait();
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  const uint4* xr = x + (int64_t)blockIdx.x * row_vec;
+  uint4 v[4], sc[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * 256;
+    if (idx < row_vec) { v[i] = __ldg(xr + idx); sc[i] = __ldg(scale + idx); }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (tid + i * 256 < row_vec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float a = bf_lo(w[j]), b = bf_hi(w[j]); ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  float n = rbf(sqrtf(tot));
+  n = rbf(n * inv_sqrt_d);
+  n = rbf(n + eps);
+  uint4* orow = out + (int64_t)blockIdx.x * row_vec;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * 256;
+    if (idx < row_vec) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[i]);
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sc[i]);
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y0 = rbf(__fdiv_rn(bf_lo(w[j]), n)), y1 = rbf(__fdiv_rn(bf_hi(w[j]), n));
+        ow[j] = pack_bf16(bf_lo(sw[j]) * y0, bf_hi(sw[j]) * y1);
+      }
+      orow[idx] = o;
+    }
+  }
+}
+
 extern "C" int evo_rmsnorm(const void* x, const void* scale, void* out, int64_t rows, int D, float eps, void* stream) {
   EVO_REQUIRE(D % 256 == 0 && D <= 8192, "evo_rmsnorm: D (%d) must be a multiple of 256 and <= 8192", D);
   if (rows == 0) return 0;
+  if (rows <= 64) {
+    EVO_CUDA(launch_pdl(rmsnorm_row_kernel, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)scale, (uint4*)out,
+                        D / 8, (float)(1.0 / sqrt((double)D)), eps));
+    return check_launch("evo_rmsnorm");
+  }
   int nvec = D / 256;
   dim3 grid((unsigned)((rows + 7) / 8)), block(256);
   float isd = (float)(1.0 / sqrt((double)D));
   if (nvec <= 16)
-    rmsnorm_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)scale, (uint4*)out, rows, nvec, isd, eps);
+    EVO_CUDA(launch_pdl(rmsnorm_kernel<16>, grid, block, 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)scale, (uint4*)out, rows, nvec, isd, eps));
   else
-    rmsnorm_kernel<32><<<grid, block, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)scale, (uint4*)out, rows, nvec, isd, eps);
+    EVO_CUDA(launch_pdl(rmsnorm_kernel<32>, grid, block, 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)scale, (uint4*)out, rows, nvec, isd, eps));
   return check_launch("evo_rmsnorm");
 }
 

@@ -224,47 +224,59 @@ __global__ void fir_state_kernel(const bf16* __restrict__ z, const bf16* __restr
   }
 }
 
-// decode step (engine.step_fir + step_iir), one thread per (b, channel)
-__global__ void hyena_step_kernel(const bf16* __restrict__ u, bf16* __restrict__ y, bf16* __restrict__ fir_state,
+// decode step (engine.step_fir + step_iir): 8 lanes per (b, channel).  Lane s owns modal state s (its pole, residue
+// and state are one coalesced 8-byte load each); lanes 0..2 run the three FIR channels (x2, x1, v); lane 0 folds the
+// eight residue products in the reference's order (sequential fma chain) and writes y.
+__global__ void __launch_bounds__(256) hyena_step_kernel(const bf16* __restrict__ u, bf16* __restrict__ y, bf16* __restrict__ fir_state,
                                   float* __restrict__ state, const bf16* __restrict__ fir_w, const bf16* __restrict__ fir_b,
                                   const bf16* __restrict__ Dskip, const float* __restrict__ poles, const float* __restrict__ residues,
                                   int B, int D, int hd) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * D) return;
-  int b = idx / D, ch = idx % D;
-  int head = ch / hd, o = ch % hd;
-  int cc[3] = {head * 3 * hd + o, head * 3 * hd + hd + o, head * 3 * hd + 2 * hd + o};   // x2, x1, v
-  long long C3 = 3LL * D;
-  float f[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    long long c = cc[k];
-    float un = __bfloat162float(u[b * C3 + c]);
+  pdl_launch_dependents(); pdl_wait();
+  static_assert(NS == 8, "one lane per modal state");
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, channel, s); B*D*8 is a multiple of 256
+  const int s = (int)(gidx & 7);
+  const long long idx = gidx >> 3;
+  const int b = (int)(idx / D), ch = (int)(idx % D);
+  const int head = ch / hd, o = ch % hd;
+  const int base = (threadIdx.x & 31) & ~7;
+  // modal operands first: their latency overlaps the FIR
+  const float2 p = reinterpret_cast<const float2*>(poles)[(long long)ch * NS + s];
+  const float2 r = reinterpret_cast<const float2*>(residues)[(long long)ch * NS + s];
+  float2* st = reinterpret_cast<float2*>(state) + idx * NS + s;
+  const float2 sv = *st;
+  const float dskip = __bfloat162float(Dskip[ch]);
+  float f = 0.f;
+  if (s < 3) {
+    const long long C3 = 3LL * D;
+    const long long c = (long long)head * 3 * hd + (long long)s * hd + o;            // x2, x1, v
+    const bf16 un_b = u[b * C3 + c];
+    const float un = __bfloat162float(un_b);
     bf16* fs = fir_state + (b * C3 + c) * 2;
-    float s0 = __bfloat162float(fs[0]), s1 = __bfloat162float(fs[1]);
-    float w0 = __bfloat162float(fir_w[c * 3 + 0]), w1 = __bfloat162float(fir_w[c * 3 + 1]), w2 = __bfloat162float(fir_w[c * 3 + 2]);
+    const bf16 s1_b = fs[1];
+    const float s0 = __bfloat162float(fs[0]), s1 = __bfloat162float(s1_b);
+    const float w0 = __bfloat162float(fir_w[c * 3 + 0]), w1 = __bfloat162float(fir_w[c * 3 + 1]), w2 = __bfloat162float(fir_w[c * 3 + 2]);
     // y = h0*u + sum(fir_state*h) + bias, bf16 tensor ops: each product / sum rounds (rp)
-    float t0 = rbf(w2 * un);
-    float t1 = rbf(rbf(s0 * w0) + rbf(s1 * w1));          // torch.sum over two bf16 products (fp32 accumulate, rp)
-    f[k] = rbf(rbf(t0 + t1) + __bfloat162float(fir_b[c]));
-    fs[0] = fs[1]; fs[1] = u[b * C3 + c];
+    const float t0 = rbf(w2 * un);
+    const float t1 = rbf(rbf(s0 * w0) + rbf(s1 * w1));          // torch.sum over two bf16 products (fp32 accumulate, rp)
+    f = rbf(rbf(t0 + t1) + __bfloat162float(fir_b[c]));
+    fs[0] = s1_b; fs[1] = un_b;
   }
-  float x2 = f[0], x = rbf(f[1] * f[2]);
+  const float x2 = __shfl_sync(0xffffffffu, f, base + 0);
+  const float x1 = __shfl_sync(0xffffffffu, f, base + 1);
+  const float v = __shfl_sync(0xffffffffu, f, base + 2);
+  const float x = rbf(x1 * v);
+  const float nr = fmaf(p.x, sv.x, fmaf(-p.y, sv.y, x));
+  const float ni = fmaf(p.x, sv.y, p.y * sv.x);
+  *st = make_float2(nr, ni);
   float acc = 0.f;
-  float2* st = reinterpret_cast<float2*>(state) + (long long)idx * NS;
 #pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    float2 p = reinterpret_cast<const float2*>(poles)[(long long)ch * NS + s];
-    float2 r = reinterpret_cast<const float2*>(residues)[(long long)ch * NS + s];
-    float2 sv = st[s];
-    float nr = fmaf(p.x, sv.x, fmaf(-p.y, sv.y, x));
-    float ni = fmaf(p.x, sv.y, p.y * sv.x);
-    st[s] = make_float2(nr, ni);
-    acc = fmaf(r.x, nr, acc); acc = fmaf(-r.y, ni, acc);
+  for (int t = 0; t < NS; ++t) {
+    const float rx = __shfl_sync(0xffffffffu, r.x, base + t), ry = __shfl_sync(0xffffffffu, r.y, base + t);
+    const float nrt = __shfl_sync(0xffffffffu, nr, base + t), nit = __shfl_sync(0xffffffffu, ni, base + t);
+    acc = fmaf(rx, nrt, acc); acc = fmaf(-ry, nit, acc);
   }
   // y = x2 * (res_state + D * x1v): D*x1v is a bf16 product (rp); the rest is fp32, cast to bf16 at the end
-  float dv = rbf(__bfloat162float(Dskip[ch]) * x);
-  y[idx] = __float2bfloat16_rn(x2 * (acc + dv));
+  if (s == 0) y[idx] = __float2bfloat16_rn(x2 * (acc + rbf(dskip * x)));
 }
 
 bool use_tma_path(const evo_hyena_params* p) {
@@ -390,10 +402,11 @@ extern "C" int evo_hyena_step(const void* u, void* y, void* fir_state, float* st
                               const float* poles, const float* residues,
                               int B, int D, int S, int nheads, void* stream) {
   EVO_REQUIRE(S == NS, "evo_hyena_step: state_size %d unsupported", S);
-  int n = B * D;
+  long long n = (long long)B * D * NS;
   if (n == 0) return 0;
-  hyena_step_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const bf16*)u, (bf16*)y, (bf16*)fir_state, state,
-      (const bf16*)fir_w, (const bf16*)fir_b, (const bf16*)Dskip, poles, residues, B, D, D / nheads);
+  EVO_REQUIRE(D % 32 == 0, "evo_hyena_step: D (%d) must be a multiple of 32", D);
+  EVO_CUDA(launch_pdl(hyena_step_kernel, dim3((unsigned)(n / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)u, (bf16*)y, (bf16*)fir_state, state,
+      (const bf16*)fir_w, (const bf16*)fir_b, (const bf16*)Dskip, poles, residues, B, D, D / nheads));
   return check_launch("evo_hyena_step");
 }
 

@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID, AttnParams, GemmParams,
+from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID, AttnParams, GemmParams, GemmSmallMParams,
                     HyenaParams, check, ptr)
 from .cache import InferenceParams, RecurrentInferenceParams
 
@@ -153,6 +153,11 @@ class StripedHyena(nn.Module):
         # tile-major weight copies for decode (GEMM variant 3): validated bit-identical but no faster on B200 (6.57 vs 6.65 ms/step:
         # the small-M GEMM is bound by bytes in flight per CTA and by too few CTAs at N=4096, not by DRAM page locality), so off
         self.decode_tiled = os.environ.get("EVO_B200_DECODE_TILED", "0") != "0"
+        # decode-step GEMMs: stream-K weight-streaming kernel (csrc/gemm_smallm.cu) for batch <= 64; "0" = the 128x64 tiles
+        self.decode_streamk = os.environ.get("EVO_B200_DECODE_STREAMK", "1") != "0"
+        # programmatic dependent launch inside a decode step (evo_set_pdl): 0 off, 1 every kernel, 2 weight-streaming GEMMs only
+        self.decode_pdl = int(os.environ.get("EVO_B200_DECODE_PDL", "0"))
+        self._smallm_ws = None
         self._tiled = None   # tile-major weight copies for the weight-streaming decode GEMMs
         self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
         self._prof = None   # set to a list to record (kind, algorithmic work, start event, end event) per kernel call
@@ -241,6 +246,20 @@ class StripedHyena(nn.Module):
                        residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
                        M=M, N=N, K=K, epilogue=epi, variant=variant)
         self._record(f"gemm/{N}x{K}/e{epi}/v{variant}", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
+
+    def _gemm_smallm(self, a, w, out, M, N, K, epi, bias=None, resid=None):
+        """Decode-step linear layer (M <= 64): stream-K weight-streaming kernel, gate epilogue fused."""
+        lib = _lib.lib()
+        need = lib.evo_gemm_smallm_workspace(M, N, K, epi)
+        ws = self._smallm_ws
+        if ws is None or ws.numel() < need or ws.device != a.device:
+            ws = self._smallm_ws = torch.zeros(max(need, lib.evo_gemm_smallm_workspace(M, 256, 64, EPI_GELU_GATE)), dtype=torch.uint8, device=a.device)
+        n_out = N // 2 if epi == EPI_GELU_GATE else N
+        p = GemmSmallMParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=n_out,
+                             bias=bias.data_ptr() if bias is not None else None,
+                             residual=resid.data_ptr() if resid is not None else None, ldr=n_out,
+                             M=M, N=N, K=K, epilogue=epi, workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+        self._record(f"gemm/{N}x{K}/e{epi}/streamk", 2.0 * M * N * K, lambda: check(lib.evo_gemm_smallm(C.byref(p), self._stream()), "evo_gemm_smallm"))
 
     def _rmsnorm(self, x, scale, out, rows):
         check(_lib.lib().evo_rmsnorm(ptr(x), ptr(scale), ptr(out), rows, self.config.hidden_size,
@@ -434,15 +453,31 @@ class StripedHyena(nn.Module):
 
     def _decode_body(self, x, pos_dev, ipd, B):
         """One token per sequence through all blocks; every launch reads the position from pos_dev."""
+        lib = _lib.lib()
+        prev = lib.evo_set_pdl(int(self.decode_pdl))
+        try:
+            return self._decode_body_impl(x, pos_dev, ipd, B)
+        finally:
+            lib.evo_set_pdl(prev)
+
+    def _decode_body_impl(self, x, pos_dev, ipd, B):
         cfg = self.config
         d, H, V = cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size
         hd = d // H
         dev = x.device
         lib = _lib.lib()
         mha_ip, hy_ip = ipd["mha"], ipd["hyena"]
-        tiled = self._ensure_tiled() if self.decode_tiled else None
+        streamk = self.decode_streamk and B <= 64
+        tiled = self._ensure_tiled() if (self.decode_tiled and not streamk) else None
         G2 = 3 if tiled is not None else 2       # weight-streaming tiles (3: tile-major weights)
         wsel = (lambda i, name, w: tiled[i][name]) if tiled is not None else (lambda i, name, w: w)
+
+        def lin(a, w, out, N, K, epi, bias=None, resid=None):
+            if streamk:
+                self._gemm_smallm(a, w, out, B, N, K, epi, bias=bias, resid=resid)
+            else:
+                self._gemm(a, w, out, B, N, K, epi, bias=bias, resid=resid, variant=G2)
+
         u = torch.empty(B, d, dtype=torch.bfloat16, device=dev)
         check(lib.evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u), B, d, V, self._stream()), "evo_embed")
         nsplit = max(1, min(16, -(-2 * torch.cuda.get_device_properties(dev).multi_processor_count // (H * B))))
@@ -453,7 +488,7 @@ class StripedHyena(nn.Module):
             if i in self._attn_idxs:
                 mha = blk.inner_mha_cls
                 qkv = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
-                self._gemm(xn, wsel(i, "in", mha.Wqkv.weight), qkv, B, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias, variant=G2)
+                lin(xn, wsel(i, "in", mha.Wqkv.weight), qkv, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
                 cache = mha_ip.key_value_memory_dict[i]
                 cos, sin = self._rope_tables(cache.shape[1], dev)
                 check(lib.evo_decode_qkv_prep(ptr(qkv), ptr(cache), ptr(cos), ptr(sin), ptr(pos_dev), B, H, hd, cache.shape[1], self._stream()), "evo_decode_qkv_prep")
@@ -462,32 +497,35 @@ class StripedHyena(nn.Module):
                 ctx = xn
                 check(lib.evo_decode_attn(ptr(qkv), ptr(cache), ptr(ctx), ptr(pos_dev), B, H, hd, cache.shape[1], nsplit,
                                           1.0 / math.sqrt(hd), ptr(ws), nws, self._stream()), "evo_decode_attn")
-                self._gemm(ctx, wsel(i, "out", mha.out_proj.weight), u2, B, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID,
-                           bias=mha.out_proj.bias, resid=u, variant=G2)
+                lin(ctx, wsel(i, "out", mha.out_proj.weight), u2, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID,
+                    bias=mha.out_proj.bias, resid=u)
             else:
                 f = blk.filter
                 z = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
-                self._gemm(xn, wsel(i, "in", blk.projections.weight), z, B, 3 * d, d, EPI_BIAS, bias=blk.projections.bias, variant=G2)
+                lin(xn, wsel(i, "in", blk.projections.weight), z, 3 * d, d, EPI_BIAS, bias=blk.projections.bias)
                 y = xn
                 check(lib.evo_hyena_step(ptr(z), ptr(y), ptr(hy_ip.fir_state_dict[i]), ptr(torch.view_as_real(hy_ip.state_dict[i])),
                                          ptr(f.short_filter_weight), ptr(f.short_filter_bias), ptr(f.D), ptr(f.poles), ptr(f.residues),
                                          B, d, cfg.state_size, H, self._stream()), "evo_hyena_step")
-                self._gemm(y, wsel(i, "out", blk.out_filter_dense.weight), u2, B, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u, variant=G2)
+                lin(y, wsel(i, "out", blk.out_filter_dense.weight), u2, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u)
             pk = self._packed[i]
             xn2 = xn
             self._rmsnorm(u2, blk.post_norm.scale, xn2, B)
-            t = torch.empty(B, 2 * pk["ipad"], dtype=torch.bfloat16, device=dev)
-            self._gemm(xn2, wsel(i, "w12", pk["w12"]), t, B, 2 * pk["ipad"], d, EPI_NONE, variant=G2)
             g = torch.empty(B, pk["ipad"], dtype=torch.bfloat16, device=dev)
-            check(lib.evo_gelu_gate_interleaved(ptr(t), ptr(g), B, pk["ipad"], self._stream()), "evo_gelu_gate_interleaved")
+            if streamk:
+                self._gemm_smallm(xn2, pk["w12"], g, B, 2 * pk["ipad"], d, EPI_GELU_GATE)
+            else:
+                t = torch.empty(B, 2 * pk["ipad"], dtype=torch.bfloat16, device=dev)
+                self._gemm(xn2, wsel(i, "w12", pk["w12"]), t, B, 2 * pk["ipad"], d, EPI_NONE, variant=G2)
+                check(lib.evo_gelu_gate_interleaved(ptr(t), ptr(g), B, pk["ipad"], self._stream()), "evo_gelu_gate_interleaved")
             u = torch.empty_like(u2)
-            self._gemm(g, wsel(i, "w3", pk["w3"]), u, B, d, pk["ipad"], EPI_RESID, resid=u2, variant=G2)
+            lin(g, wsel(i, "w3", pk["w3"]), u, d, pk["ipad"], EPI_RESID, resid=u2)
         if self.norm is not None:
             xn = torch.empty_like(u)
             self._rmsnorm(u, self.norm.scale, xn, B)
             u = xn
         logits = torch.empty(B, V, dtype=torch.bfloat16, device=dev)
-        self._gemm(u, tiled["unembed"] if tiled is not None else self.unembed.weight, logits, B, V, d, EPI_NONE, variant=G2)
+        lin(u, tiled["unembed"] if tiled is not None else self.unembed.weight, logits, V, d, EPI_NONE)
         return logits
 
     def _decode_forward(self, x, ipd):

@@ -66,6 +66,31 @@ typedef struct {
                                     3 = like 2 with W given tile-major: (N/64, K/64, 64, 64), i.e. W.view(N/64,64,K/64,64).permute(0,2,1,3) */
 } evo_gemm_params;
 int evo_gemm(const evo_gemm_params* p, void* stream);
+/* Decode-step linear layer (M <= 64 rows): the same C = epilogue(A . W^T) with the same rounding points, as a
+ * weight-streaming kernel (csrc/gemm_smallm.cu): swap-AB tcgen05 tiles (128 W rows x M), stream-K over all SMs,
+ * deterministic fix-up through `workspace`, weight prefetch ahead of the programmatic-dependent-launch wait.
+ * EVO_EPI_GELU_GATE is fused here (C is (M, N/2)); replaces ParallelGatedMLP / nn.Linear at L == 1
+ * (evo/generation.py:152 step path).  workspace: evo_gemm_smallm_workspace() bytes, zero-filled ONCE by the caller
+ * (the per-tile counters in it reset themselves); one workspace may serve every call on a stream. */
+typedef struct {
+  const void* A; int64_t lda;
+  const void* W;                 /* (N, K) row-major; GELU_GATE: rows interleaved [l1 | l2] per 256 */
+  void* C; int64_t ldc;
+  const void* bias;
+  const void* residual; int64_t ldr;
+  int64_t M, N, K;               /* M <= 64, N % 256 == 0, K % 64 == 0 */
+  int epilogue;                  /* EVO_EPI_* */
+  void* workspace; size_t workspace_bytes;
+} evo_gemm_smallm_params;
+size_t evo_gemm_smallm_workspace(int64_t M, int64_t N, int64_t K, int epilogue);
+int evo_gemm_smallm(const evo_gemm_smallm_params* p, void* stream);
+/* Programmatic dependent launch for the decode step.  0 = off (default); 1 = every decode-step kernel is launched with
+ * programmatic stream serialization; 2 = only evo_gemm_smallm is (its weight prefetch then overlaps the small kernel or
+ * the GEMM tail in front of it).  Every decode-step kernel begins with griddepcontrol.launch_dependents and waits
+ * (griddepcontrol.wait) before it first touches dependent data.  Process-wide switch; returns the previous value. */
+int evo_set_pdl(int level);
+/* debug hook: device buffer of gridDim.x * 16 int64 time stamps written by evo_gemm_smallm (NULL = off) */
+void evo_debug_smallm_trace(void* buf);
 /* test comparator only (cuBLASLt, plain C = A.W^T [+bias]); never on the product path */
 int evo_gemm_cublaslt_reference(const evo_gemm_params* p, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -52,7 +52,7 @@ def meanerr(a, b):
 
 
 # ------------------------------------------------------------------ glue kernels: bit exact
-@pytest.mark.parametrize("D,rows", [(256, 37), (4096, 129), (4096, 0)])
+@pytest.mark.parametrize("D,rows", [(256, 37), (4096, 129), (4096, 0), (4096, 16), (8192, 3), (512, 64), (4096, 65)])
 def test_rmsnorm_bit_exact(D, rows):
     torch.manual_seed(D + rows)
     x = (torch.randn(rows, D) * 3).bfloat16()
@@ -279,6 +279,70 @@ def test_gemm_tile_major_weights_variant3():
         assert torch.equal(out, ref)
 
 
+def _gemm_smallm(a, w, M, N, K, epi, bias=None, resid=None, ws=None):
+    lib = _lib.lib()
+    n_out = N // 2 if epi == _lib.EPI_GELU_GATE else N
+    out = torch.full((M, n_out), float("nan"), dtype=torch.bfloat16, device=DEV)
+    if ws is None:
+        ws = torch.zeros(lib.evo_gemm_smallm_workspace(M, N, K, epi), dtype=torch.uint8, device=DEV)
+    p = _lib.GemmSmallMParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=n_out,
+                              bias=bias.data_ptr() if bias is not None else None, residual=resid.data_ptr() if resid is not None else None, ldr=n_out,
+                              M=M, N=N, K=K, epilogue=epi, workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+    _lib.check(lib.evo_gemm_smallm(C.byref(p), stream()), "evo_gemm_smallm")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M", [1, 16, 17, 40, 64])
+@pytest.mark.parametrize("N,K", [(256, 64), (512, 4096), (768, 256), (4096, 4096), (12288, 4096), (22016, 4096), (4096, 11008)])
+def test_gemm_smallm_streamk_all_epilogues(M, N, K):
+    """Decode-step weight-streaming kernel (swap-AB tiles, stream-K + ordered fix-up): every epilogue against an fp64-accumulated
+    reference, the workspace counters return to zero, and repeated launches give identical bits (deterministic reduction)."""
+    if M not in (16, 17) and N * K > 4096 * 4096:
+        pytest.skip("large shapes are covered at M = 16 / 17")
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+    bias = (torch.randn(N, device=DEV) * 0.2).bfloat16()
+    resid = torch.randn(M, N, device=DEV).bfloat16()
+    acc = a.double() @ w.double().T
+    lib = _lib.lib()
+    ws = torch.zeros(max(lib.evo_gemm_smallm_workspace(M, N, K, e) for e in range(5)), dtype=torch.uint8, device=DEV)
+
+    def close(out, ref, mult=1.0, eq=None):
+        assert not torch.isnan(out.float()).any()
+        assert maxerr(out, ref) <= mult * BF16_EPS * max(1.0, ref.abs().max().item())
+        assert (out == ref.to(out.dtype)).float().mean() > (eq or (0.98 if K <= 1024 else 0.90))
+
+    close(_gemm_smallm(a, w, M, N, K, _lib.EPI_NONE, ws=ws), acc.bfloat16())
+    o1 = _gemm_smallm(a, w, M, N, K, _lib.EPI_BIAS, bias=bias, ws=ws)
+    close(o1, (acc + bias.double()).bfloat16())
+    close(_gemm_smallm(a, w, M, N, K, _lib.EPI_BIAS_RESID, bias=bias, resid=resid, ws=ws), ((acc + bias.double()).bfloat16().double() + resid.double()).bfloat16())
+    close(_gemm_smallm(a, w, M, N, K, _lib.EPI_RESID, resid=resid, ws=ws), (acc.bfloat16().double() + resid.double()).bfloat16())
+    wv = w.view(N // 256, 2, 128, K)
+    z1 = (a.double() @ wv[:, 0].reshape(-1, K).double().T).bfloat16()
+    z2 = (a.double() @ wv[:, 1].reshape(-1, K).double().T).bfloat16()
+    ref = (torch.nn.functional.gelu(z1.float()).bfloat16().float() * z2.float()).bfloat16()
+    close(_gemm_smallm(a, w, M, N, K, _lib.EPI_GELU_GATE, ws=ws), ref, mult=2.0, eq=0.97 if K <= 1024 else 0.88)
+    assert int(ws[:16384].view(torch.int32).abs().sum().item()) == 0          # tile counters reset themselves
+    for _ in range(3):
+        assert torch.equal(_gemm_smallm(a, w, M, N, K, _lib.EPI_BIAS, bias=bias, ws=ws), o1)
+    # same rounding points as the throughput tiles: results agree to an accumulation-order ulp
+    big = G._gemm(a, w, M, N, K, _lib.EPI_BIAS, 1, bias=bias)
+    assert (big == o1).float().mean() > 0.97
+
+
+def test_gemm_smallm_rejects_bad_arguments():
+    a = torch.zeros(65, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(256, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(_lib.EvoError, match="must be in"):
+        _gemm_smallm(a, w, 65, 256, 64, _lib.EPI_NONE)
+    with pytest.raises(_lib.EvoError, match="workspace too small"):
+        _gemm_smallm(a, w, 16, 256, 64, _lib.EPI_NONE, ws=torch.zeros(64, dtype=torch.uint8, device=DEV))
+    with pytest.raises(_lib.EvoError, match="multiple of 256"):
+        _gemm_smallm(a, torch.zeros(128, 64, dtype=torch.bfloat16, device=DEV), 16, 128, 64, _lib.EPI_NONE)
+
+
 def test_gemm_rejects_bad_shapes():
     a = torch.zeros(8, 64, dtype=torch.bfloat16, device=DEV)
     w = torch.zeros(100, 64, dtype=torch.bfloat16, device=DEV)
@@ -451,6 +515,43 @@ def test_stateful_prefill_then_steps_equals_stateless():
         assert maxerr(s[:, 0], full[:, t]) <= 0.03 * scale
         d["mha"].seqlen_offset += 1
         d["hyena"].seqlen_offset += 1
+
+
+def test_decode_streamk_pdl_paths_agree():
+    """Decode step through (a) the 128x64 tiles without programmatic dependent launch, (b) the stream-K kernel without it,
+    (c) stream-K + PDL (levels 1 and 2) inside the CUDA graph: same logits up to accumulation order, (c) repeatable bit for bit."""
+    cfg, sd, m = _tiny()
+    torch.manual_seed(2)
+    ids = (torch.randint(0, 4, (3, 90)) * 3 + 65).to(DEV)
+
+    def run(streamk, pdl, graph):
+        m.decode_streamk, m.decode_pdl, m.decode_graph, m._decode = streamk, pdl, graph, None
+        d = m.initialize_inference_params()
+        d["mha"].max_batch_size, d["mha"].max_seqlen = 3, 128
+        _, d = m(ids[:, :60], inference_params_dict=d)
+        d["mha"].seqlen_offset = d["hyena"].seqlen_offset = 60
+        outs = []
+        for t in range(60, 90):
+            s, d = m(ids[:, t:t + 1], inference_params_dict=d)
+            outs.append(s[:, 0].clone())
+            d["mha"].seqlen_offset += 1
+            d["hyena"].seqlen_offset += 1
+        return torch.stack(outs, 1)
+
+    try:
+        saved = (m.decode_streamk, m.decode_pdl, m.decode_graph)
+        a = run(False, 0, False)
+        b = run(True, 0, False)
+        c = run(True, 1, True)
+        c2 = run(True, 1, True)
+        e = run(True, 2, True)
+    finally:
+        m.decode_streamk, m.decode_pdl, m.decode_graph = saved
+        m._decode = None
+    scale = a.float().abs().max().item()
+    assert maxerr(b, a) <= 0.03 * scale and maxerr(c, a) <= 0.03 * scale
+    assert torch.equal(c, c2)
+    assert torch.equal(b, c) and torch.equal(b, e)        # PDL and graph replay change scheduling only
 
 
 def test_public_api_scoring_and_generation():

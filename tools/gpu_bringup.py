@@ -424,7 +424,8 @@ def stage_perf_decode():
     e = (dec[:, -8:].float() - full[:, P + N - 8:].float()).abs()
     emit("perf_decode", B=B, prompt=P, steps=N, prefill_s=t_prefill, prefill_nt_s=B * P / t_prefill, first_step_ms=times[0] * 1e3, capture_step_ms=times[1] * 1e3,
          steady_ms_per_step=steady * 1e3, decode_nt_s=B / steady, decode_vs_stateless_max=e.max().item(), logit_scale=full.float().abs().max().item(),
-         weight_stream_floor_ms=12.9e9 / 6566.4e9 * 1e3, eager_breakdown=breakdown)
+         weight_stream_floor_ms=12.9e9 / 6566.4e9 * 1e3, eager_breakdown=breakdown,
+         env={k: os.environ.get(k) for k in ("EVO_B200_DECODE_STREAMK", "EVO_B200_DECODE_PDL", "EVO_B200_SMALLM_SMEM_KB", "EVO_B200_DECODE_GRAPH")})
 
 
 if __name__ == "__main__":
