@@ -1,6 +1,6 @@
 """bench.py — nucleotides/sec of the Evo-1 7B forward on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 8k|131k|1k|32k] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 8k|131k|1k|32k|gen] [--impl ours|reference]
 
 Workload "8k" (default, BASELINE.json configs[1]): evo-1-8k-base scoring forward, batch 8 x
 8192 nt of synthetic uniform ACGT (+BOS => L = 8193), bf16, random-init weights of the 7B
@@ -33,6 +33,8 @@ WORKLOADS = {
     "1k": dict(model="evo-1-8k-base", batch=64, nt=1024, desc="evo-1-8k-base 7B scoring forward, batch 64 x 1024 nt (+BOS), bf16"),
     "32k": dict(model="evo-1-131k-base", batch=2, nt=32768, desc="evo-1-131k-base 7B forward, batch 2 x 32768 nt (+BOS), bf16"),
     "131k": dict(model="evo-1-131k-base", batch=1, nt=131072, desc="evo-1-131k-base 7B forward, batch 1 x 131072 nt, bf16"),
+    # BASELINE configs[3] (secondary line, not the headline): cached generation, one step = one new nucleotide per sequence
+    "gen": dict(model="evo-1.5-8k-base", batch=16, nt=4096, desc="evo-1.5-8k-base 7B cached generation, batch 16, prompt 4096 nt, greedy decode steps, bf16"),
 }
 
 
@@ -292,6 +294,100 @@ def bench_ours(args, wl):
         dist.destroy_process_group()
 
 
+def bench_generate(args, wl):
+    """Secondary workload: the L == 1 step path (recurrent Hyena state + KV cache) after a 4096-nt prefill.
+    value = generated nt/s with the state resident on the GPU (greedy token fed back on the device);
+    e2e = evo_b200.generate() from prompt strings to generated strings (prefill included).  Rank-local (replicas)."""
+    import torch
+    import evo_b200
+    from evo_b200 import _lib, CharLevelTokenizer
+    from evo_b200.models import load_checkpoint
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    torch.cuda.set_device(dev)
+    steps = args.steps if args.steps is not None else 64
+    warmup = max(3, args.warmup if args.warmup is not None else 4)
+    model = load_checkpoint(wl["model"], device=dev, random_init=True, seed=0)
+    tok = CharLevelTokenizer(512)
+    B, P = wl["batch"], wl["nt"]
+    seqs = synthetic_seqs(B, P, seed=rank)
+    ids = torch.tensor([tok.tokenize(s) for s in seqs], dtype=torch.long, device=dev)
+    d = model.initialize_inference_params()
+    d["mha"].max_batch_size = d["hyena"].max_batch_size = B
+    logits, d = model(ids, inference_params_dict=d)
+    d["mha"].seqlen_offset = d["hyena"].seqlen_offset = P
+    nxt = logits[:, -1].argmax(-1, keepdim=True)
+
+    def step():
+        nonlocal nxt, d
+        lg, d = model(nxt, inference_params_dict=d)
+        nxt = lg[:, -1].argmax(-1, keepdim=True)
+        d["mha"].seqlen_offset += 1
+        d["hyena"].seqlen_offset += 1
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    lib = _lib.lib()
+    lib.evo_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.evo_launch_count()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = B * world * steps / (ms / 1e3)
+    # end to end: prompts as strings -> generated strings, through the reference-shaped API (prefill + n_tokens steps)
+    n_new = 32
+    del d
+    torch.cuda.empty_cache()
+    evo_b200.generate(seqs, model, tok, n_tokens=4, top_k=1, cached_generation=True, verbose=0, device=dev, force_prompt_threshold=P)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out, _ = evo_b200.generate(seqs, model, tok, n_tokens=n_new, top_k=1, cached_generation=True, verbose=0, device=dev, force_prompt_threshold=P)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        peaks = measured_peaks()
+        cfg = model.config
+        n_attn = len(cfg.attn_layer_idxs)
+        weight_bytes = sum(p.numel() * p.element_size() for p in model.parameters())
+        ctx = P + warmup + steps / 2.0
+        kv_bytes = n_attn * B * ctx * 2 * cfg.hidden_size * 2
+        ach = (weight_bytes + kv_bytes) / (ms / steps / 1e3) / 1e9
+        print(json.dumps({
+            "metric": "generated nucleotides/sec, evo-1.5 7B cached decode", "value": value, "unit": "nt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic uniform ACGT prompts, random-init weights of the 7B architecture",
+            "config": {"workload": wl["desc"], "global_batch": B * world, "seq_len": P, "parallelism": f"replicas x{world}",
+                       "l2": "every step streams 12.9 GB of weights and ~3.2 GB of KV cache (L2 = 126 MB)",
+                       "decode": {"streamk": model.decode_streamk, "pdl": model.decode_pdl, "cuda_graph": model.decode_graph}},
+            "clocks": clocks.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": B * world * n_new / dt, "unit": "nt/s", "h2d_bytes_per_step": B * P * 8 // n_new, "d2h_bytes_per_step": B * 4,
+                    "api": f"evo_b200.generate(prompts, n_tokens={n_new}, top_k=1, cached_generation=True): 4096-nt prefill + {n_new} steps, strings in / strings out"},
+            "roofline": {"kernel": "decode step (gemm_smallm_kernel weight stream + decode_attn_tma_kernel KV stream)", "bound": "hbm", "achieved": ach,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                         "algorithmic_bytes_per_step": weight_bytes + kv_bytes, "peak_source": peaks["source"]},
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -304,6 +400,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         bench_reference(args, wl)
+    elif args.workload == "gen":
+        bench_generate(args, wl)
     else:
         bench_ours(args, wl)
 

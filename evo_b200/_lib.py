@@ -52,6 +52,7 @@ SIGNATURES = {
     "evo_abi_version": (C.c_int, []),
     "evo_launch_count": (C.c_int64, []),
     "evo_reset_launch_count": (None, []),
+    "evo_note_graph_replay": (None, [C.c_int64]),
     "evo_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "evo_rmsnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
     "evo_gemm": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),

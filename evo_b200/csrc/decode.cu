@@ -4,6 +4,7 @@
 // Python).
 #include "common.cuh"
 #include "../../include/evo_b200.h"
+#include <cstdlib>
 
 using namespace evo;
 
@@ -127,6 +128,124 @@ __global__ void __launch_bounds__(DT) decode_attn_kernel(const bf16* __restrict_
   if (tid == 0) { part_ml[pidx * 2] = M; part_ml[pidx * 2 + 1] = L; }
 }
 
+// ---- decode attention, TMA-fed (default when max_seqlen % 64 == 0) ----
+// The per-thread-row kernel above issues 16-byte loads whose 32 lanes touch 32 different 128-byte lines (K rows of
+// one head are 16 KB apart): the L1 tag stage caps it near 3 TB/s.  Here a producer warp streams 64-key K and V tiles
+// of one (b, h) into a 3-stage shared-memory ring with TMA (box {128, 1, 64} of the cache viewed as
+// (hd, 2H, B*S)), and four independent compute warps each own 16 keys of every tile: QK with lane = (key, half
+// row) reading rotated 16-byte chunks (conflict-free), a warp-local online softmax, PV with lane = 4 output dims.
+// The warps' (m, l, o) states are merged once at the end; splits are merged by decode_attn_merge_kernel.
+constexpr int TK = 64;                 // keys per tile
+constexpr int AST = 3;                 // ring stages
+constexpr int TILE_BYTES = TK * HD * 2;          // 16 KB (K) + 16 KB (V) per stage
+constexpr int ATT2_SMEM = AST * 2 * TILE_BYTES + 1024;
+__global__ void __launch_bounds__(160, 2) decode_attn_tma_kernel(const __grid_constant__ CUtensorMap tm, const bf16* __restrict__ qkv,
+                                                                 float* __restrict__ part_o, float* __restrict__ part_ml,
+                                                                 const long long* __restrict__ pos_ptr, int H, long long S, int nsplit, float scale) {
+  pdl_launch_dependents(); pdl_wait();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + AST * 2 * TILE_BYTES);
+  uint64_t* empty = full + AST;
+  bf16* qb = reinterpret_cast<bf16*>(empty + AST);                   // 256 B
+  float* red = reinterpret_cast<float*>(qb + HD);                      // [4][2] (m, l) then [4][128] o, overlaid on stage 0 after the loop
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long nk = min(*pos_ptr + 1, S);
+  long long per = (nk + nsplit - 1) / nsplit;
+  per = (per + TK - 1) / TK * TK;                                      // splits start on tile boundaries
+  const long long k0 = (long long)sp * per, k1 = min(nk, k0 + per);
+  const int ntiles = k1 > k0 ? (int)((k1 - k0 + TK - 1) / TK) : 0;
+  if (tid == 0) {
+    for (int i = 0; i < AST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (tid < HD) qb[tid] = qkv[((long long)(b * 3) * H + h) * HD + tid];
+  __syncthreads();
+
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], 2 * TILE_BYTES);
+        const int row = (int)((long long)b * S + k0 + (long long)t * TK);
+        tma_load_3d(smem + stage * 2 * TILE_BYTES, &tm, &full[stage], 0, h, row);
+        tma_load_3d(smem + stage * 2 * TILE_BYTES + TILE_BYTES, &tm, &full[stage], 0, H + h, row);
+        if (++stage == AST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int key = lane & 15, half = lane >> 4;
+    int stage = 0; uint32_t phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(&full[stage], phase);
+      const uint8_t* Ks = smem + stage * 2 * TILE_BYTES;
+      const uint8_t* Vs = Ks + TILE_BYTES;
+      const long long jg = k0 + (long long)t * TK + warp * 16 + key;
+      float sd = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int cc = (c + lane) & 7;                                 // rotated: a quarter-warp covers all 32 banks
+        const uint4 kv = *reinterpret_cast<const uint4*>(Ks + (warp * 16 + key) * (HD * 2) + half * 128 + cc * 16);
+        const uint4 qv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(qb) + half * 128 + cc * 16);
+        const uint32_t* kw = reinterpret_cast<const uint32_t*>(&kv);
+        const uint32_t* qw = reinterpret_cast<const uint32_t*>(&qv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sd = fmaf(bf_lo(qw[e]), bf_lo(kw[e]), sd); sd = fmaf(bf_hi(qw[e]), bf_hi(kw[e]), sd); }
+      }
+      sd += __shfl_xor_sync(0xffffffffu, sd, 16);
+      sd = jg < k1 ? sd * scale : -INFINITY;
+      float mx = sd;
+#pragma unroll
+      for (int x = 8; x > 0; x >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, x));
+      const float mn = fmaxf(m, mx);
+      if (mn != -INFINITY) {                                           // warp-uniform
+        const float alpha = __expf(m - mn), pe = __expf(sd - mn);
+        l = l * alpha + (half == 0 ? pe : 0.f);
+        const float pb = rbf(pe);                                      // P rounded to bf16 before the PV product, like the prefill kernel
+        o0 *= alpha; o1 *= alpha; o2 *= alpha; o3 *= alpha;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float pj = __shfl_sync(0xffffffffu, pb, j);
+          if (pj != 0.f) {                                             // masked keys (and underflowed ones) contribute nothing; garbage rows never reach the FMA
+            const uint2 vv = *reinterpret_cast<const uint2*>(Vs + (warp * 16 + j) * (HD * 2) + lane * 8);
+            o0 = fmaf(pj, bf_lo(vv.x), o0); o1 = fmaf(pj, bf_hi(vv.x), o1);
+            o2 = fmaf(pj, bf_lo(vv.y), o2); o3 = fmaf(pj, bf_hi(vv.y), o3);
+          }
+        }
+        m = mn;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == AST) { stage = 0; phase ^= 1; }
+    }
+#pragma unroll
+    for (int x = 16; x > 0; x >>= 1) l += __shfl_xor_sync(0xffffffffu, l, x);
+  }
+  __syncthreads();                                                      // every tile consumed: stage 0 is free for the merge
+  float* red_o = reinterpret_cast<float*>(smem);                       // [4][128]
+  if (warp < 4) {
+    if (lane == 0) { red[warp * 2] = m; red[warp * 2 + 1] = l; }
+    *reinterpret_cast<float4*>(red_o + warp * HD + lane * 4) = make_float4(o0, o1, o2, o3);
+  }
+  __syncthreads();
+  if (tid < HD) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, red[w * 2]);
+    float acc = 0.f, L = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float sc = red[w * 2] == -INFINITY ? 0.f : __expf(red[w * 2] - M);
+      acc += red_o[w * HD + tid] * sc;
+      L += red[w * 2 + 1] * sc;
+    }
+    const long long pidx = ((long long)b * H + h) * nsplit + sp;
+    part_o[pidx * HD + tid] = acc;
+    if (tid == 0) { part_ml[pidx * 2] = M; part_ml[pidx * 2 + 1] = L; }
+  }
+}
+
 __global__ void decode_attn_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, bf16* __restrict__ out,
                                          int H, int nsplit) {
   pdl_launch_dependents(); pdl_wait();
@@ -174,6 +293,23 @@ extern "C" int evo_decode_attn(const void* qkv, const void* cache, void* out, co
   EVO_REQUIRE(workspace && workspace_bytes >= evo_decode_attn_workspace(B, H, nsplit), "evo_decode_attn: workspace too small");
   float* part_o = (float*)workspace;
   float* part_ml = part_o + (size_t)B * H * nsplit * HD;
+  static const bool force_v1 = getenv("EVO_B200_DECODE_ATTN_V1") != nullptr;
+  if (max_seqlen % TK == 0 && !force_v1 && (long long)B * max_seqlen < (1LL << 31)) {
+    CUtensorMap tm;
+    const uint64_t dims[3] = {(uint64_t)HD, (uint64_t)(2 * H), (uint64_t)B * (uint64_t)max_seqlen};
+    const uint64_t str[2] = {(uint64_t)HD * 2, (uint64_t)2 * H * HD * 2};
+    const uint32_t box[3] = {(uint32_t)HD, 1, (uint32_t)TK};
+    int rc = make_tmap_nd_bf16(&tm, cache, 3, dims, str, box, false);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) { EVO_CUDA(cudaFuncSetAttribute(decode_attn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM)); attr_done = true; }
+    EVO_CUDA(launch_pdl(decode_attn_tma_kernel, dim3(H, B, nsplit), dim3(160), (size_t)ATT2_SMEM, (cudaStream_t)stream, tm, (const bf16*)qkv, part_o, part_ml,
+                        (const long long*)pos, H, (long long)max_seqlen, nsplit, softmax_scale));
+    rc = check_launch("evo_decode_attn");
+    if (rc) return rc;
+    EVO_CUDA(launch_pdl(decode_attn_merge_kernel, dim3(H, B), dim3(HD), 0, (cudaStream_t)stream, (const float*)part_o, (const float*)part_ml, (bf16*)out, H, nsplit));
+    return check_launch("evo_decode_attn_merge");
+  }
   EVO_CUDA(launch_pdl(decode_attn_kernel, dim3(H, B, nsplit), dim3(DT), 0, (cudaStream_t)stream, (const bf16*)qkv, (const bf16*)cache, part_o, part_ml,
                       (const long long*)pos, H, max_seqlen, nsplit, softmax_scale));
   int rc = check_launch("evo_decode_attn");

@@ -156,7 +156,7 @@ class StripedHyena(nn.Module):
         # decode-step GEMMs: stream-K weight-streaming kernel (csrc/gemm_smallm.cu) for batch <= 64; "0" = the 128x64 tiles
         self.decode_streamk = os.environ.get("EVO_B200_DECODE_STREAMK", "1") != "0"
         # programmatic dependent launch inside a decode step (evo_set_pdl): 0 off, 1 every kernel, 2 weight-streaming GEMMs only
-        self.decode_pdl = int(os.environ.get("EVO_B200_DECODE_PDL", "0"))
+        self.decode_pdl = int(os.environ.get("EVO_B200_DECODE_PDL", "2"))
         self._smallm_ws = None
         self._tiled = None   # tile-major weight copies for the weight-streaming decode GEMMs
         self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
@@ -480,7 +480,7 @@ class StripedHyena(nn.Module):
 
         u = torch.empty(B, d, dtype=torch.bfloat16, device=dev)
         check(lib.evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u), B, d, V, self._stream()), "evo_embed")
-        nsplit = max(1, min(16, -(-2 * torch.cuda.get_device_properties(dev).multi_processor_count // (H * B))))
+        nsplit = max(1, min(16, -(-8 * torch.cuda.get_device_properties(dev).multi_processor_count // (H * B))))   # >= ~4 waves of 2 CTAs/SM
         for i, blk in enumerate(self.blocks):
             xn = torch.empty_like(u)
             self._rmsnorm(u, blk.pre_norm.scale, xn, B)
@@ -559,9 +559,13 @@ class StripedHyena(nn.Module):
         if st["graph"] is None:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
+            n0 = _lib.lib().evo_launch_count()
             with torch.cuda.graph(g):
                 st["logits"] = self._decode_body(st["x"], st["pos"], ipd, B)
             st["graph"] = g
+            st["launches"] = _lib.lib().evo_launch_count() - n0      # counted while capturing, when nothing ran: undo, then count per replay
+            _lib.lib().evo_note_graph_replay(-st["launches"])
         st["graph"].replay()
+        _lib.lib().evo_note_graph_replay(st["launches"])
         st["steps"] += 1
         return st["logits"].clone().view(B, 1, -1)

@@ -31,6 +31,10 @@ int evo_abi_version(void);
 /* #launches of evo_b200 kernels since the last evo_reset_launch_count() (bench: gpu_launches) */
 int64_t evo_launch_count(void);
 void evo_reset_launch_count(void);
+/* a CUDA-graph replay launches the kernels captured in it without passing through this library: the host adds the
+ * number of launches recorded at capture time, once per replay (and subtracts the ones counted while capturing,
+ * when nothing ran), so that evo_launch_count() stays truthful */
+void evo_note_graph_replay(int64_t launches);
 
 /* ---- embedding gather: VocabParallelEmbedding.embed (evo/models.py:136 pins the key) ----
  * ids: int32 or int64 (ids_are_i64), n tokens; table (vocab, D) bf16; out (n, D) bf16. */

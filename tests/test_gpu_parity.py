@@ -402,9 +402,12 @@ def test_attention_kv_cache_form(variant):
         assert maxerr(o, ref[:, off:off + Lq]) <= 4 * BF16_EPS * max(1.0, ref.abs().max().item())
 
 
-def test_decode_attention_with_device_position():
-    """evo_decode_qkv_prep + evo_decode_attn (position read from device memory) vs the oracle."""
-    B, H, Lc = 3, 2, 640
+@pytest.mark.parametrize("Lc", [640, 600])
+def test_decode_attention_with_device_position(Lc):
+    """evo_decode_qkv_prep + evo_decode_attn (position read from device memory) vs the oracle.  Lc = 640 takes the TMA-fed
+    kernel (64-key tiles), Lc = 600 the per-thread-row kernel.  Cache rows past the position hold NaN (the reference
+    allocates its cache with torch.empty, mha.py:349): they must not leak into the result."""
+    B, H = 3, 2
     lib = _lib.lib()
     torch.manual_seed(9)
     full = torch.randn(B, 600, 3, H, 128).bfloat16()
@@ -412,9 +415,9 @@ def test_decode_attention_with_device_position():
     q = O.apply_rotary(full[:, :, 0], cos[:600], sin[:600])
     k = O.apply_rotary(full[:, :, 1], cos[:600], sin[:600])
     ref = O.causal_attention(q, k, full[:, :, 2]).reshape(B, 600, H * 128)
-    cache = torch.zeros(B + 1, Lc, 2, H, 128, dtype=torch.bfloat16)
     cosd, sind = cos.to(DEV), sin.to(DEV)
-    for pos in (0, 1, 130, 599):
+    for pos in (0, 1, 63, 64, 127, 130, 599):
+        cache = torch.full((B + 1, Lc, 2, H, 128), float("nan"), dtype=torch.bfloat16)
         cache[:B, :pos, 0] = k[:, :pos]
         cache[:B, :pos, 1] = full[:, :pos, 2]
         cd = cache.to(DEV)
@@ -422,12 +425,13 @@ def test_decode_attention_with_device_position():
         posd = torch.tensor([pos], dtype=torch.int64, device=DEV)
         _lib.check(lib.evo_decode_qkv_prep(_lib.ptr(qkv), _lib.ptr(cd), _lib.ptr(cosd), _lib.ptr(sind), _lib.ptr(posd), B, H, 128, Lc, stream()))
         assert (cd[:B, pos, 0].cpu() == k[:, pos]).float().mean() > 0.995 and torch.equal(cd[:B, pos, 1].cpu(), full[:, pos, 2])
-        for nsplit in (1, 4):
+        for nsplit in (1, 3, 4):
             n = lib.evo_decode_attn_workspace(B, H, nsplit)
             ws = torch.empty(n, dtype=torch.uint8, device=DEV)
             out = torch.empty(B, H * 128, dtype=torch.bfloat16, device=DEV)
             _lib.check(lib.evo_decode_attn(_lib.ptr(qkv), _lib.ptr(cd), _lib.ptr(out), _lib.ptr(posd), B, H, 128, Lc, nsplit,
                                            1 / math.sqrt(128), _lib.ptr(ws), n, stream()))
+            assert not torch.isnan(out.float()).any()
             assert maxerr(out, ref[:, pos]) <= 4 * BF16_EPS * max(1.0, ref.abs().max().item())
     _lib.check(lib.evo_advance_position(_lib.ptr(posd), 3, stream()))
     assert posd.item() == 602

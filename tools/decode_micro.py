@@ -122,6 +122,16 @@ def main():
                 for i in range(3):
                     launch(i)
                 torch.cuda.synchronize()
+        Bc, S, Hh = M, 8192, 32
+        cache = torch.randn(Bc, S, 2, Hh, 128, device=DEV).bfloat16()
+        qkv = torch.randn(Bc, 3, Hh, 128, device=DEV).bfloat16()
+        ctxo = torch.empty(Bc, Hh * 128, dtype=torch.bfloat16, device=DEV)
+        posd = torch.full((1,), 4095, dtype=torch.int64, device=DEV)
+        nws = lib.evo_decode_attn_workspace(Bc, Hh, 3)
+        wsa = torch.empty(nws, dtype=torch.uint8, device=DEV)
+        for _ in range(2):
+            _lib.check(lib.evo_decode_attn(_lib.ptr(qkv), _lib.ptr(cache), _lib.ptr(ctxo), _lib.ptr(posd), Bc, Hh, 128, S, 3, 1.0 / math.sqrt(128), _lib.ptr(wsa), nws, stream()))
+        torch.cuda.synchronize()
         return
     for name, N, K, epi in shapes:
         copies = max(2, min(8, int(400e6 // (N * K * 2)) + 1))
@@ -157,7 +167,7 @@ def main():
     qkv = torch.randn(Bc, 3, H, 128, device=DEV).bfloat16()
     ctxo = torch.empty(Bc, H * 128, dtype=torch.bfloat16, device=DEV)
     posd = torch.full((1,), ctx - 1, dtype=torch.int64, device=DEV)
-    for nsplit in (1, 2, 4, 8):
+    for nsplit in (1, 2, 3, 4, 8):
         nws = lib.evo_decode_attn_workspace(Bc, H, nsplit)
         wsa = torch.empty(nws, dtype=torch.uint8, device=DEV)
         fn = lambda: [_lib.check(lib.evo_decode_attn(_lib.ptr(qkv), _lib.ptr(cache), _lib.ptr(ctxo), _lib.ptr(posd), Bc, H, 128, S, nsplit,
