@@ -37,6 +37,11 @@ extern "C" int evo_embed(const void* ids, int ids_are_i64, const void* table, vo
 // One warp per row; the row stays in registers between the reduction and the scale.
 // Rounding points follow the reference's bf16 tensor ops (layers.RMSNorm.forward):
 //   n = bf16(||x||) ; n = bf16(n * D^-1/2) ; n = bf16(n + eps) ; y = bf16(x / n) ; out = bf16(scale * y)
+// The quotient is computed as x * rcp(n) (one reciprocal per row instead of 2*D/32 IEEE divisions per lane, which made the
+// kernel instruction-bound at ~50 % of HBM speed).  This is exact after the bf16 rounding: x and n have 8-bit
+// significands, so x/n is either exactly representable or at least 2^-17 (relative) away from every bf16 rounding
+// midpoint (a 9-bit significand m with x = n*m would need x to have >= 9 significant bits), while x * rcp_rn(n)
+// is within 2^-23 of x/n: both round to the same bf16.
 template <int MAXV>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ x, const uint4* __restrict__ scale,
                                                       uint4* __restrict__ out, int64_t rows, int nvec_per_lane,
@@ -63,6 +68,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ 
   float n = rbf(sqrtf(ss));
   n = rbf(n * inv_sqrt_d);
   n = rbf(n + eps);
+  const float rinv = __frcp_rn(n);          // see the note above rmsnorm_kernel: bf16(x * (1/n)) == bf16(x / n) for bf16 x, n
   uint4* orow = out + row * row_vec;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const uint4* __restrict__ 
       uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float y0 = rbf(__fdiv_rn(bf_lo(w[j]), n)), y1 = rbf(__fdiv_rn(bf_hi(w[j]), n));
+        float y0 = rbf(bf_lo(w[j]) * rinv), y1 = rbf(bf_hi(w[j]) * rinv);
         ow[j] = pack_bf16(bf_lo(sw[j]) * y0, bf_hi(sw[j]) * y1);
       }
       orow[i * 32 + lane] = o;
@@ -115,6 +121,7 @@ __global__ void __launch_bounds__(256) rmsnorm_row_kernel(const uint4* __restric
   float n = rbf(sqrtf(tot));
   n = rbf(n * inv_sqrt_d);
   n = rbf(n + eps);
+  const float rinv = __frcp_rn(n);
   uint4* orow = out + (int64_t)blockIdx.x * row_vec;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(256) rmsnorm_row_kernel(const uint4* __restric
       uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float y0 = rbf(__fdiv_rn(bf_lo(w[j]), n)), y1 = rbf(__fdiv_rn(bf_hi(w[j]), n));
+        float y0 = rbf(bf_lo(w[j]) * rinv), y1 = rbf(bf_hi(w[j]) * rinv);
         ow[j] = pack_bf16(bf_lo(sw[j]) * y0, bf_hi(sw[j]) * y1);
       }
       orow[idx] = o;

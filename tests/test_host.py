@@ -206,3 +206,20 @@ def test_load_checkpoint_from_local_safetensors(tmp_path):
         load_checkpoint("evo-1-8k-base", config_path=str(cfg_path), model_dir=str(bad))
     with pytest.raises(FileNotFoundError):
         load_checkpoint("evo-1-8k-base", config_path=str(cfg_path), model_dir=str(tmp_path / "nope"))
+
+
+def test_rmsnorm_reciprocal_multiply_is_exact_after_bf16_rounding():
+    """csrc/elementwise.cu computes bf16(x / n) as bf16(x * rcp(n)).  Exhaustive over every pair of bf16 significands
+    (and a spread of exponents): the two agree bit for bit, also when the reciprocal is one fp32 ulp off."""
+    import torch
+
+    def all_bf16(e_lo, e_hi):
+        sig = torch.arange(128, dtype=torch.float32) / 128 + 1.0
+        ex = torch.arange(e_lo, e_hi, dtype=torch.float32)
+        return (sig[None, :] * torch.pow(torch.tensor(2.0), ex)[:, None]).reshape(-1)
+
+    x, n = all_bf16(-4, 4), all_bf16(-20, 6)
+    q = (x[:, None] / n[None, :]).bfloat16()
+    r = 1.0 / n
+    assert torch.equal((x[:, None] * r[None, :]).bfloat16(), q)
+    assert torch.equal((x[:, None] * torch.nextafter(r, torch.tensor(float("inf")))[None, :]).bfloat16(), q)
