@@ -28,11 +28,13 @@ from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID
 from .cache import InferenceParams, RecurrentInferenceParams
 
 # kernel variants (see include/evo_b200.h); overridable for experiments
-# measured on B200: in isolated bursts the 2-CTA 256x256 tile is the faster one for the plain epilogues
-# (profiles/r01_perf_kernels_call3.jsonl), but inside the power-capped 0.8 s step the 1-CTA 128x256 tile
-# sustains ~2 % more (profiles/r01_bench_8k_variants_call5.json, same box back to back)
-GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "1"))
-GEMM_VARIANT_GATE = int(os.environ.get("EVO_B200_GEMM_VARIANT_GATE", "1"))
+# measured on B200, same box, interleaved A/B inside the power-capped 0.7 s step (profiles/r01_gemm_variant_ab_call32.txt):
+# the 2-CTA 256x256 tile (variant 0) gives 93.1-93.2 k nt/s against 88.3-88.5 k for the 1-CTA 128x256 tile -- each CTA
+# stages 32 KB instead of 48 KB per k-block, so the same FLOPs cost less operand traffic and power.  (An early-round
+# comparison had the 1-CTA tile ahead by 2 %; that was before the traffic-aware rasterisation and with a
+# release.cluster arrive in the pair's epilogue.)
+GEMM_VARIANT = int(os.environ.get("EVO_B200_GEMM_VARIANT", "0"))
+GEMM_VARIANT_GATE = int(os.environ.get("EVO_B200_GEMM_VARIANT_GATE", "0"))
 # attention: 2 = ping-pong kernel (two query tiles per CTA, P in TMEM): 0.89-1.07 PFLOP/s vs 0.86-1.07 for variant 1
 ATTN_VARIANT = int(os.environ.get("EVO_B200_ATTN_VARIANT", "2"))
 
