@@ -223,3 +223,12 @@ def test_rmsnorm_reciprocal_multiply_is_exact_after_bf16_rounding():
     r = 1.0 / n
     assert torch.equal((x[:, None] * r[None, :]).bfloat16(), q)
     assert torch.equal((x[:, None] * torch.nextafter(r, torch.tensor(float("inf")))[None, :]).bfloat16(), q)
+
+
+def test_prepare_batch_empty_list_raises_like_the_reference():
+    """evo/scoring.py:21 takes max() of the lengths: an empty batch is a ValueError there, and here."""
+    tok = evo_b200.CharLevelTokenizer(512)
+    with pytest.raises(ValueError):
+        evo_b200.prepare_batch([], tok, device="cpu")
+    ids, lengths = evo_b200.prepare_batch(["", "AC"], tok, device="cpu")      # an empty sequence is padded, length 0
+    assert ids.tolist() == [[0, 1, 1], [0, 65, 67]] and lengths == [0, 2]
