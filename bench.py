@@ -139,6 +139,9 @@ def cpu_baseline(model_name, target_seconds=15.0, threads=None):
         L = int(min(2048, 16 * target_seconds / t16))
         L = max(32, (L // 32) * 32)
         t = run(L)
+        if t < 0.6 * target_seconds and L < 2048:          # throughput grows with L (weights amortised): resize once from the real run
+            L = max(32, (int(min(2048, L * target_seconds / t)) // 32) * 32)
+            t = run(L)
     return {"value": L / t, "unit": "nt/s", "cores": threads, "kind": "port", "host_cpus": ncpu, "cpu_dtype": str(dtype).replace("torch.", ""),
             "sample": f"oracle (stripedhyena 0.2.2 restatement) {str(dtype).replace('torch.', '')} on CPU, 7B shape, batch 1 x {L} nt, {t:.1f} s"}, m, run
 
