@@ -1,15 +1,16 @@
 """Sweep the GEMM rasterisation knobs (experiments): each setting runs in its own process because the
-library reads EVO_B200_GEMM_GROUP / EVO_B200_GEMM_RASTER_N once.   python tools/gemm_raster_sweep.py"""
+library reads EVO_B200_GEMM_GROUP / EVO_B200_GEMM_RASTER_N once.   python tests/harness/gemm_raster_sweep.py"""
 import json
 import os
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
-    from tools import gpu_bringup as G
+    import gpu_bringup as G
     G._imports()
     import torch
     dev = "cuda:0"

@@ -1,7 +1,7 @@
 """GPU bring-up / diagnostics harness (development tool, run under gpurun).
 
-    python tools/gpu_bringup.py                 # all stages, each in its own subprocess + timeout
-    python tools/gpu_bringup.py --stage gemm1   # one stage inline
+    python tests/harness/gpu_bringup.py                 # all stages, each in its own subprocess + timeout
+    python tests/harness/gpu_bringup.py --stage gemm1   # one stage inline
 
 Every stage compares the CUDA kernels with the CPU oracle (and with torch-on-GPU where that
 is a useful second opinion) and appends JSON lines to gpurun_out/bringup.jsonl, so a hang
@@ -17,7 +17,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)

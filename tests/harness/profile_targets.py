@@ -1,11 +1,12 @@
 """Small single-kernel drivers for ncu captures (development tool).
 
-    ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 2 -o gpurun_out/gemm python tools/profile_targets.py gemm1
+    ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -c 2 -o gpurun_out/gemm python tests/harness/profile_targets.py gemm1
 """
 import sys
 import os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tools import gpu_bringup as G
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import gpu_bringup as G
 
 G._imports()
 import torch  # noqa: E402

@@ -25,7 +25,8 @@ pytestmark = pytest.mark.gpu
 from oracle import stripedhyena_oracle as O          # noqa: E402  (tests may use the oracle)
 from evo_b200 import _lib                             # noqa: E402
 from evo_b200.stripedhyena import StripedHyena, dotdict  # noqa: E402
-from tools import gpu_bringup as G                    # noqa: E402  (shared launch helpers)
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
+import gpu_bringup as G                               # noqa: E402  (shared launch helpers, tests/harness/)
 
 G._imports()
 DEV = "cuda:0"
