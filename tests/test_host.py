@@ -232,3 +232,49 @@ def test_prepare_batch_empty_list_raises_like_the_reference():
         evo_b200.prepare_batch([], tok, device="cpu")
     ids, lengths = evo_b200.prepare_batch(["", "AC"], tok, device="cpu")      # an empty sequence is padded, length 0
     assert ids.tolist() == [[0, 1, 1], [0, 65, 67]] and lengths == [0, 2]
+
+
+def test_streamk_partition_invariants():
+    """Python mirror of the index math in csrc/gemm_smallm.cu (range_start / cta_of / slot choice): for many
+    (tiles, k-blocks, grid) the ranges tile [0, total) without gaps, every partial segment gets a slot nobody else uses,
+    and the contributor window [c_first, c_last] of a tile is exactly the set of CTAs with a segment in it."""
+    def range_start(c, total, parts):
+        return (c * total) // parts
+
+    def cta_of(it, total, parts):
+        c = (it * parts) // total
+        while c + 1 < parts and range_start(c + 1, total, parts) <= it:
+            c += 1
+        while c > 0 and range_start(c, total, parts) > it:
+            c -= 1
+        return c
+
+    rng = np.random.default_rng(0)
+    cases = [(96, 64, 148), (32, 64, 148), (86, 64, 148), (32, 172, 148), (4, 64, 32), (1, 1, 1), (2, 1, 2), (3, 7, 2)]
+    cases += [(int(rng.integers(1, 200)), int(rng.integers(1, 200)), 148) for _ in range(40)]
+    for n_tiles, KB, sms in cases:
+        total = n_tiles * KB
+        parts = max(1, min(sms, total // 8))
+        assert total * sms < 2 ** 31
+        segs = {}                                            # tile -> list of (cta, k0, k1, slot)
+        covered = 0
+        for c in range(parts):
+            b, e = range_start(c, total, parts), range_start(c + 1, total, parts)
+            assert b == covered and e > b
+            covered = e
+            it, first_tile = b, b // KB
+            while it < e:
+                tile, k0 = it // KB, it % KB
+                k1 = min(KB, k0 + (e - it))
+                if not (k0 == 0 and k1 == KB):
+                    segs.setdefault(tile, []).append((c, k0, k1, 2 * c + (0 if tile == first_tile else 1)))
+                it += k1 - k0
+        assert covered == total
+        slots = [s for v in segs.values() for (_, _, _, s) in v]
+        assert len(slots) == len(set(slots)) and all(s < 2 * parts for s in slots)
+        for tile, v in segs.items():
+            c_first, c_last = cta_of(tile * KB, total, parts), cta_of((tile + 1) * KB - 1, total, parts)
+            assert [c for (c, _, _, _) in v] == list(range(c_first, c_last + 1))
+            assert sum(k1 - k0 for (_, k0, k1, _) in v) == KB
+            for (c, _, _, s) in v:                           # the finisher recomputes every contributor's slot the same way
+                assert s == 2 * c + (0 if range_start(c, total, parts) // KB == tile else 1)
