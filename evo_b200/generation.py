@@ -1,15 +1,20 @@
-"""Autoregressive generation over the stateful `model(x, inference_params_dict=...)` call;
-entry points and semantics of the reference's evo/generation.py (Generator.generate
-:38-204, generate :207-297): the first `force_prompt_threshold` prompt tokens are prefilled
-in one parallel forward, the remaining prompt tokens are teacher-forced one step at a time,
-then `num_tokens` tokens are sampled.  Returned scores keep the reference's alignment
-(quirk Q3).  Unlike the reference, a prompt of any length can be prefilled in
-one pass (pass force_prompt_threshold >= prompt length): the Hyena prefill state comes out
-of the scan kernel, there is no (B, D, 8, 2L) FFT temporary."""
+"""Token-by-token generation on top of the stateful call `model(x, inference_params_dict=d)`.
+
+Same entry points, arguments and observable behaviour as the reference's evo/generation.py
+(class Generator :38-204, function generate :207-297):
+  * the first `force_prompt_threshold` prompt tokens go through one parallel forward, the rest of
+    the prompt is teacher-forced one step at a time, then `num_tokens` tokens are sampled;
+  * the position bookkeeping the caller-visible state objects expose (`seqlen_offset` on both
+    holders) follows the reference, including its jump to the full prompt length after a
+    truncated prefill (quirk Q1) and its report-only EOS check (Q2);
+  * the per-sequence "scores" keep the reference's one-off alignment (Q3).
+What differs is underneath: the Hyena prefill state comes out of the scan kernel, so a prompt of
+any length can be prefilled in one pass (`force_prompt_threshold >= len(prompt)`); there is no
+(B, D, 8, 2L) FFT temporary that forces the 128-token cap."""
 from __future__ import annotations
 
 import sys
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -19,138 +24,142 @@ from .stripedhyena.sample import sample
 from .tokenizer import CharLevelTokenizer
 
 
+def _gb(device) -> float:
+    return torch.cuda.memory_allocated(device=device) / 1e9 if torch.cuda.is_available() else 0.0
+
+
 class Generator:
     def __init__(self, model, tokenizer: CharLevelTokenizer, top_k: int = 50, top_p: float = 0.7, temperature: float = 1.0):
-        self.model = model
-        self.tokenizer = tokenizer
-        self.top_k = top_k
-        self.top_p = top_p
-        self.temperature = temperature
+        self.model, self.tokenizer = model, tokenizer
+        self.top_k, self.top_p, self.temperature = top_k, top_p, temperature
         self.untils = ["\n\n"]
 
+    # -- pieces of generate() -------------------------------------------------------------
+    def _state_for(self, batch: int, device, cached: bool, given: Optional[dict]):
+        """(state dict or None, cached?, already prefilled?).  A caller-held state is moved to the
+        prompt's device and resumed (evo/generation.py:105-114); otherwise a fresh one is made."""
+        if given is not None:
+            holders = (given["mha"].key_value_memory_dict, given["hyena"].fir_state_dict, given["hyena"].state_dict)
+            for store in holders:
+                for key in list(store):
+                    store[key] = store[key].to(device)
+            return given, True, True
+        if not cached:
+            return None, False, False
+        fresh = self.model.initialize_inference_params()
+        for holder in (fresh["mha"], fresh["hyena"]):
+            holder.max_batch_size = batch
+        return fresh, True, False
+
+    @staticmethod
+    def _advance(state: dict, full_prompt_len: int) -> None:
+        attn, rec = state["mha"], state["hyena"]
+        if attn.seqlen_offset == 0:
+            # first step after the prefill: the reference sets the FULL prompt length even if only
+            # `force_prompt_threshold` tokens were prefilled (Q1) -- reproduced, not repaired
+            attn.seqlen_offset = rec.seqlen_offset = full_prompt_len
+        else:
+            attn.seqlen_offset += 1
+            rec.seqlen_offset += 1
+
+    def _pick(self, last_logits: torch.Tensor) -> torch.Tensor:
+        return sample(last_logits, top_k=self.top_k, top_p=self.top_p, temperature=self.temperature)
+
+    # -- public ---------------------------------------------------------------------------
     def generate(self, device: str, input_string: str = None, input_ids: torch.Tensor = None, num_tokens: int = 32,
                  cached_generation: bool = True, force_prompt_threshold: int = 128, print_generation: bool = True,
                  verbose: bool = False, skip_special_tokens: bool = False, stop_at_eos: bool = True,
                  max_seqlen: int = None, inference_params_dict: dict = None) -> Tuple[torch.Tensor, torch.Tensor, dict]:
-        tok = self.tokenizer
-        eos_ids = torch.tensor([tok.eos], dtype=torch.long, device=device)
-        if input_ids is None:
-            prompt = torch.tensor(tok.tokenize(input_string), dtype=torch.long, device=device).unsqueeze(0)
-        else:
-            prompt = input_ids
-        x = prompt if max_seqlen is None else prompt[:, -max_seqlen:]
+        tk = self.tokenizer
+        full_prompt = input_ids if input_ids is not None else torch.tensor(tk.tokenize(input_string), dtype=torch.long, device=device)[None]
+        window = full_prompt if max_seqlen is None else full_prompt[:, -max_seqlen:]
         num_tokens = int(num_tokens)
-        batch, prompt_len = x.shape
+        n_seq, n_prompt = window.shape
+        dev = window.device
 
-        n_forced = max(0, prompt_len - force_prompt_threshold)
-        forced = x[:, force_prompt_threshold:] if n_forced else None
-        if n_forced:
-            x = x[:, :force_prompt_threshold]
+        # prompt split: [prefilled in parallel | teacher-forced step by step]
+        tail = window[:, force_prompt_threshold:] if n_prompt > force_prompt_threshold else window[:, :0]
+        x = window[:, :force_prompt_threshold] if tail.shape[1] else window
+        n_tail = tail.shape[1]
 
-        out_ids = torch.empty(batch, num_tokens, dtype=torch.long, device=x.device)
-        out_logits = torch.empty(batch, num_tokens, tok.vocab_size, dtype=torch.float, device=x.device)
-
-        prefilled = False
-        if inference_params_dict is not None:      # resume from a caller-held state (evo/generation.py:105-114)
-            cached_generation, prefilled = True, True
-            mha, hy = inference_params_dict["mha"], inference_params_dict["hyena"]
-            for store in (mha.key_value_memory_dict, hy.fir_state_dict, hy.state_dict):
-                for k in list(store):
-                    store[k] = store[k].to(x.device)
-        elif cached_generation:
-            inference_params_dict = self.model.initialize_inference_params()
-            inference_params_dict["mha"].max_batch_size = batch
-            inference_params_dict["hyena"].max_batch_size = batch
+        picked = torch.empty(n_seq, num_tokens, dtype=torch.long, device=dev)
+        kept_logits = torch.empty(n_seq, num_tokens, tk.vocab_size, dtype=torch.float, device=dev)
+        eos = torch.tensor([tk.eos], dtype=torch.long, device=device)
+        state, cached_generation, resumed = self._state_for(n_seq, dev, cached_generation, inference_params_dict)
 
         if verbose:
-            print(f"Memory after tokenization: {torch.cuda.memory_allocated(device=x.device) / 1e9} GB")
-            print("Starting generation...")
-            print("Prompt: " + input_string if input_string is not None else f"Prompt ids: {input_ids} {input_ids.shape}")
+            what = f"prompt {input_string!r}" if input_string is not None else f"prompt ids {tuple(input_ids.shape)}"
+            print(f"[generate] {what}; {_gb(dev):.2f} GB allocated; prefill {x.shape[1]} + forced {n_tail} + new {num_tokens}")
 
-        total = n_forced + num_tokens
-        step = -1
-        for step in range(total):
-            stepping = prefilled or (cached_generation and step > 0)
-            if stepping:
+        last_step = -1
+        for last_step in range(n_tail + num_tokens):
+            one_token = resumed or (cached_generation and last_step > 0)
+            if one_token:
                 x = x[:, -1:]
-                mha, hy = inference_params_dict["mha"], inference_params_dict["hyena"]
-                if mha.seqlen_offset == 0:
-                    # the reference jumps to the FULL prompt length here even when only
-                    # `force_prompt_threshold` tokens were prefilled (quirk Q1); kept as is
-                    mha.seqlen_offset = hy.seqlen_offset = prompt.shape[-1]
-                else:
-                    mha.seqlen_offset += 1
-                    hy.seqlen_offset += 1
-
+                self._advance(state, full_prompt.shape[-1])
             with torch.inference_mode():
-                logits, inference_params_dict = self.model(x, inference_params_dict=inference_params_dict)
-            last = logits[:, -1]
+                logits, state = self.model(x, inference_params_dict=state)
+            head = logits[:, -1]
+            token = tail[:, last_step] if last_step < n_tail else self._pick(head)
 
-            if step < n_forced:
-                nxt = forced[:, step]
-            else:
-                nxt = sample(last, top_k=self.top_k, top_p=self.top_p, temperature=self.temperature)
+            if stop_at_eos and num_tokens >= 2 and bool((picked[0, -2:] == eos).all()):
+                print("Stopping generation at EOS")              # report only, as in the reference (Q2)
+            if print_generation and verbose and n_seq == 1:
+                print(tk.detokenize([token.item()]), end=" ")
 
-            if stop_at_eos and num_tokens >= 2 and bool((out_ids[0, -2:] == eos_ids).all()):
-                print("Stopping generation at EOS")   # the reference only reports it (quirk Q2)
-            if print_generation and verbose and batch == 1:
-                print(f"{tok.detokenize([nxt.item()])}", end=" ")
+            k = last_step - n_tail
+            if k >= 0:
+                kept_logits[:, k], picked[:, k] = head, token
+            x = token[:, None] if one_token else torch.cat([x, token[:, None]], dim=-1)
 
-            slot = step - n_forced
-            if slot >= 0:
-                out_logits[:, slot] = last
-                out_ids[:, slot] = nxt
-
-            x = nxt[:, None] if stepping else torch.cat([x, nxt[:, None]], dim=-1)
-
+        done = last_step + 1
         if verbose:
-            text = tok.detokenize_batch(out_ids[:, : step + 1])
-            for until in self.untils:
-                if until in text:
-                    text = text.split(until)[0]
+            shown = tk.detokenize_batch(picked[:, :done])
+            for stop in self.untils:
+                if stop in shown:
+                    shown = shown.split(stop)[0]
                     break
-            print(f"\nInput: {input_string}, Output: {text}")
-            print(f"Memory after generation: {torch.cuda.memory_allocated(device=x.device) / 1e9} GB")
-
-        return out_ids[:, : step + 1], out_logits[:, : step + 1], inference_params_dict
+            print(f"\n[generate] in: {input_string} | out: {shown} | {_gb(dev):.2f} GB allocated")
+        return picked[:, :done], kept_logits[:, :done], state
 
 
 def generate(prompt_seqs: List[str], model, tokenizer: CharLevelTokenizer, n_tokens: int = 100, temperature: float = 0.0,
              top_k: int = 1, top_p: float = 1.0, batched: bool = True, prepend_bos: bool = False,
              cached_generation: bool = False, force_prompt_threshold: int = 128, verbose: int = 1,
              device: str = "cuda:0", **kwargs) -> Tuple[List[str], List[float]]:
-    """Generate from a list of prompts; equal-length prompts are batched."""
+    """Sequences and mean log-likelihood "scores" for a list of prompts.  Prompts of one common
+    length run as one batch; anything else falls back to one prompt at a time (with a note on stderr)."""
     model.eval()
-    g = Generator(model, tokenizer, top_k=top_k, top_p=top_p, temperature=temperature)
-    same_len = all(len(s) == len(prompt_seqs[0]) for s in prompt_seqs)
-    if batched and same_len:
-        groups = [prompt_seqs]
+    engine = Generator(model, tokenizer, top_k=top_k, top_p=top_p, temperature=temperature)
+    uniform = len({len(p) for p in prompt_seqs}) <= 1
+    if batched and uniform:
+        work = [list(prompt_seqs)]
     else:
+        if verbose and not uniform:
+            sys.stderr.write("Note: Prompts are of different lengths.\n")
         if verbose:
-            if not same_len:
-                sys.stderr.write("Note: Prompts are of different lengths.\n")
             sys.stderr.write("Note: Will not do batched generation.\n")
-        groups = [[s] for s in prompt_seqs]
+        work = [[p] for p in prompt_seqs]
 
-    seqs_out: List[str] = []
-    scores_out: List[float] = []
-    for grp in groups:
-        ids = prepare_batch(grp, tokenizer, prepend_bos=prepend_bos, device=device)[0]
-        out_ids, logits, _ = g.generate(input_ids=ids, num_tokens=n_tokens, cached_generation=cached_generation,
-                                        force_prompt_threshold=force_prompt_threshold, device=device,
-                                        print_generation=(verbose > 1), verbose=(verbose > 1), stop_at_eos=False)
-        if verbose > 1:
-            print("input_ids.shape", ids.shape)
-            print("output_ids.shape", out_ids.shape)
-            print("logits.shape", logits.shape)
-        texts = tokenizer.detokenize_batch(out_ids)
-        if len(texts) != ids.shape[0]:
+    chatty = verbose > 1
+    texts: List[str] = []
+    scores: List[float] = []
+    for group in work:
+        ids, _ = prepare_batch(group, tokenizer, prepend_bos=prepend_bos, device=device)
+        new_ids, new_logits, _ = engine.generate(device=device, input_ids=ids, num_tokens=n_tokens, stop_at_eos=False,
+                                                 cached_generation=cached_generation, force_prompt_threshold=force_prompt_threshold,
+                                                 print_generation=chatty, verbose=chatty)
+        if chatty:
+            print(f"[generate] ids {tuple(ids.shape)} -> new ids {tuple(new_ids.shape)}, logits {tuple(new_logits.shape)}")
+        decoded = tokenizer.detokenize_batch(new_ids)
+        if len(decoded) != ids.shape[0]:
             raise AssertionError("batch size mismatch after detokenisation")
-        seqs_out += list(texts)
-        lp = logits_to_logprobs(logits, out_ids).float().cpu().numpy()   # alignment as in the reference (Q3)
-        scores_out += [float(np.mean(lp[i])) for i in range(ids.shape[0])]
+        texts.extend(decoded)
+        # logits_to_logprobs(trim_bos=True) pairs logits[i] with token[i+1]: the reference's alignment (Q3)
+        per_token = logits_to_logprobs(new_logits, new_ids).float().cpu().numpy()
+        scores.extend(float(np.mean(row)) for row in per_token)
 
     if verbose:
-        for seq, score, prompt in zip(seqs_out, scores_out, prompt_seqs):
-            print(f'Prompt: "{prompt}",\tOutput: "{seq}",\tScore: {score}')
-    return seqs_out, scores_out
+        for prompt, text, score in zip(prompt_seqs, texts, scores):
+            print(f'Prompt: "{prompt}",\tOutput: "{text}",\tScore: {score}')
+    return texts, scores
