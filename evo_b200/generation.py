@@ -115,10 +115,7 @@ class Generator:
         done = last_step + 1
         if verbose:
             shown = tk.detokenize_batch(picked[:, :done])
-            for stop in self.untils:
-                if stop in shown:
-                    shown = shown.split(stop)[0]
-                    break
+            shown = [t.split(stop)[0] if stop in t else t for t in shown for stop in self.untils[:1]]
             print(f"\n[generate] in: {input_string} | out: {shown} | {_gb(dev):.2f} GB allocated")
         return picked[:, :done], kept_logits[:, :done], state
 
