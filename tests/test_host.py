@@ -278,3 +278,32 @@ def test_streamk_partition_invariants():
             assert sum(k1 - k0 for (_, k0, k1, _) in v) == KB
             for (c, _, _, s) in v:                           # the finisher recomputes every contributor's slot the same way
                 assert s == 2 * c + (0 if range_start(c, total, parts) // KB == tile else 1)
+
+
+def test_generate_function_batches_equal_lengths_and_scores_like_the_reference(capsys):
+    """evo/generation.py:207-297: equal-length prompts run as one batch, ragged ones one by one (with notes on stderr);
+    the returned score is mean(logits_to_logprobs(new_logits, new_ids)) with the reference's trim_bos alignment (Q3)."""
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=2)
+    tok = CharLevelTokenizer(512)
+    model = _OracleAsModel(cfg, sd)
+    texts, scores = evo_b200.generate(["ACGT", "TTGA"], model, tok, n_tokens=4, top_k=1, cached_generation=True, verbose=0, device="cpu")
+    assert len(texts) == 2 and all(len(t) == 4 for t in texts) and len(scores) == 2
+    assert model.calls[0][0] == (2, 4)                              # one batched prefill
+    # the same prompts one at a time give the same greedy continuations and the same scores
+    model1 = _OracleAsModel(cfg, sd)
+    texts1, scores1 = evo_b200.generate(["ACGT", "TTGA"], model1, tok, n_tokens=4, top_k=1, cached_generation=True, verbose=1,
+                                        batched=False, device="cpu")
+    err = capsys.readouterr().err
+    assert "Will not do batched generation" in err and "different lengths" not in err
+    assert texts1 == texts and np.allclose(scores1, scores, atol=1e-4)
+    assert model1.calls[0][0] == (1, 4)
+    # score definition: recompute from a direct Generator call
+    g = Generator(_OracleAsModel(cfg, sd), tok, top_k=1)
+    ids, _ = prepare_batch(["ACGT"], tok, prepend_bos=False, device="cpu")
+    new_ids, new_logits, _ = g.generate(device="cpu", input_ids=ids, num_tokens=4, cached_generation=True, print_generation=False, stop_at_eos=False)
+    want = logits_to_logprobs(new_logits, new_ids).float().mean().item()
+    assert abs(want - scores[0]) < 1e-4
+    # ragged prompts: falls back to one at a time and says why
+    evo_b200.generate(["ACGT", "TT"], _OracleAsModel(cfg, sd), tok, n_tokens=2, top_k=1, cached_generation=False, verbose=1, device="cpu")
+    assert "different lengths" in capsys.readouterr().err
