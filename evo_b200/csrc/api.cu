@@ -75,13 +75,19 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
   return 0;
 }
 
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int device_sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
+  static int cache[64] = {0};
+  const int dev = current_device();
+  if (dev < 0) return 148;
+  if (dev < 64 && cache[dev]) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev < 64) cache[dev] = n;
   return n;
 }
 

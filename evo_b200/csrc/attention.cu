@@ -336,72 +336,7 @@ int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], con
   return 0;
 }
 
-// ---- plain CUDA-core comparator (tests only): one warp per query row
-__global__ void attn_simple_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, bf16* __restrict__ out,
-                                   long long q_tok, long long kv_tok, long long q_batch, long long kv_batch,
-                                   int B, long long Lq, long long Lk, int H, long long q_pos0, float scale) {
-  __shared__ float qs[4][HD];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long row = (long long)blockIdx.x * 4 + w;         // (b, h, i)
-  const bool active = row < (long long)B * H * Lq;
-  long long i = active ? row % Lq : 0;
-  int h = active ? (int)((row / Lq) % H) : 0;
-  int b = active ? (int)(row / (Lq * H)) : 0;
-  const bf16* qp = q + b * q_batch + i * q_tok + (long long)h * HD;
-  for (int d = lane; d < HD; d += 32) qs[w][d] = __bfloat162float(qp[d]);
-  __syncwarp();
-  if (!active) return;
-  const long long pos = q_pos0 + i;
-  const long long nk = min(Lk, pos + 1);
-  float m = -INFINITY, l = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long j0 = 0; j0 < nk; j0 += 32) {
-    long long j = j0 + lane;
-    float s = -INFINITY;
-    if (j < nk) {
-      const bf16* kp = k + b * kv_batch + j * kv_tok + (long long)h * HD;
-      float acc = 0.f;
-      for (int d = 0; d < HD; ++d) acc = fmaf(qs[w][d], __bfloat162float(kp[d]), acc);
-      s = acc * scale;
-    }
-    float mc = s;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, off));
-    float mn = fmaxf(m, mc);
-    float alpha = (m == -INFINITY) ? 0.f : expf(m - mn);
-    float p = (j < nk) ? expf(s - mn) : 0.f;
-    float ps = p;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
-    l = l * alpha + ps;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) o[t] *= alpha;
-    float pb = rbf(p);
-    for (int jj = 0; jj < 32; ++jj) {
-      float pj = __shfl_sync(0xffffffffu, pb, jj);
-      if (j0 + jj < nk) {
-        const bf16* vp = v + b * kv_batch + (j0 + jj) * kv_tok + (long long)h * HD;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) o[t] = fmaf(pj, __bfloat162float(vp[lane + 32 * t]), o[t]);
-      }
-    }
-    m = mn;
-  }
-  bf16* op = out + ((b * Lq + i) * H + h) * HD;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) op[lane + 32 * t] = __float2bfloat16_rn(o[t] / l);
-}
-
 }  // namespace
-
-extern "C" int evo_attn_fwd_simple(const evo_attn_params* p, void* stream) {
-  EVO_REQUIRE(p->hd == HD, "evo_attn_fwd_simple: head_dim %d unsupported", p->hd);
-  long long rows = (long long)p->B * p->H * p->Lq;
-  if (rows == 0) return 0;
-  attn_simple_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
-      (const bf16*)p->q, (const bf16*)p->k, (const bf16*)p->v, (bf16*)p->out, p->q_tok_stride, p->kv_tok_stride,
-      p->q_batch_stride, p->kv_batch_stride, p->B, p->Lq, p->Lk, p->H, p->q_pos0, p->softmax_scale);
-  return check_launch("evo_attn_fwd_simple");
-}
 
 int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const evo_attn_params* p, cudaStream_t st);   // attention_pp.cu
 
@@ -452,12 +387,12 @@ extern "C" int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* work
   a.scale_log2 = p->softmax_scale * 1.4426950408889634f;
   dim3 grid((unsigned)((p->Lq + BQ - 1) / BQ), p->H, p->B);
   if (variant == 1) {
-    static bool done = false;
-    if (!done) { EVO_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); done = true; }
+    static unsigned long long done = 0;
+    if ((rc = ensure_dyn_smem(attn_fwd_kernel<true>, ATT_SMEM, done))) return rc;
     attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, a);
   } else {
-    static bool done = false;
-    if (!done) { EVO_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM)); done = true; }
+    static unsigned long long done = 0;
+    if ((rc = ensure_dyn_smem(attn_fwd_kernel<false>, ATT_SMEM, done))) return rc;
     attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, a);
   }
   return check_launch("evo_attn_fwd");

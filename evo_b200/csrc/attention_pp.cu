@@ -279,8 +279,8 @@ int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
   a.out = (bf16*)p->out; a.B = p->B; a.H = p->H; a.Lq = p->Lq; a.Lk = p->Lk; a.q_pos0 = p->q_pos0;
   a.scale_log2 = p->softmax_scale * 1.4426950408889634f;
   a.n_qblk = (int)((p->Lq + BQ - 1) / BQ);
-  static bool done = false;
-  if (!done) { EVO_CUDA(cudaFuncSetAttribute(attn_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); done = true; }
+  static unsigned long long done = 0;
+  { int rc_ = ensure_dyn_smem(attn_pp_kernel, SMEM, done); if (rc_) return rc_; }
   dim3 grid((unsigned)((a.n_qblk + 1) / 2), p->H, p->B);
   attn_pp_kernel<<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, a);
   return check_launch("evo_attn_fwd(pp)");

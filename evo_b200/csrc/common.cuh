@@ -237,7 +237,20 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, bool swizzle128);
 
-int device_sm_count();
+int device_sm_count();     // of the CURRENT device (cached per device ordinal)
+int current_device();      // cudaGetDevice, -1 on error
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: `mask` keeps one "done" bit per device
+// ordinal, so a process that drives a second GPU (model moved to cuda:1) raises the limit there too.
+template <typename K>
+inline int ensure_dyn_smem(K kern, int bytes, unsigned long long& mask) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64 || !((mask >> dev) & 1ull)) {
+    EVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev >= 0 && dev < 64) mask |= 1ull << dev;
+  }
+  return 0;
+}
 int pdl_level();         // evo_set_pdl(): 0 off, 1 all decode-step kernels, 2 weight-streaming GEMM only
 
 // Programmatic dependent launch: every kernel that may be launched with the attribute calls pdl_wait() before it

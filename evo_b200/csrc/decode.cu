@@ -301,8 +301,8 @@ extern "C" int evo_decode_attn(const void* qkv, const void* cache, void* out, co
     const uint32_t box[3] = {(uint32_t)HD, 1, (uint32_t)TK};
     int rc = make_tmap_nd_bf16(&tm, cache, 3, dims, str, box, false);
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) { EVO_CUDA(cudaFuncSetAttribute(decode_attn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM)); attr_done = true; }
+    static unsigned long long attr_done = 0;
+    if ((rc = ensure_dyn_smem(decode_attn_tma_kernel, ATT2_SMEM, attr_done))) return rc;
     EVO_CUDA(launch_pdl(decode_attn_tma_kernel, dim3(H, B, nsplit), dim3(160), (size_t)ATT2_SMEM, (cudaStream_t)stream, tm, (const bf16*)qkv, part_o, part_ml,
                         (const long long*)pos, H, (long long)max_seqlen, nsplit, softmax_scale));
     rc = check_launch("evo_decode_attn");

@@ -242,23 +242,6 @@ extern "C" int evo_kv_append(const void* qkv, void* cache, int B, int64_t L, int
   return check_launch("evo_kv_append");
 }
 
-// ------------------------------------------------------------------ add
-__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, int64_t nvec) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nvec) return;
-  uint4 x = a[i], y = b[i], o;
-  const uint32_t *xw = (const uint32_t*)&x, *yw = (const uint32_t*)&y;
-  uint32_t* ow = (uint32_t*)&o;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) ow[j] = pack_bf16(bf_lo(xw[j]) + bf_lo(yw[j]), bf_hi(xw[j]) + bf_hi(yw[j]));
-  out[i] = o;
-}
-extern "C" int evo_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
-  EVO_REQUIRE(n % 8 == 0, "evo_add: n must be a multiple of 8");
-  if (n == 0) return 0;
-  add_kernel<<<(unsigned)((n / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
-  return check_launch("evo_add");
-}
 
 // ------------------------------------------------------------------ scoring epilogue
 // out[r] = log_softmax(logits[r, :])[target[r]], fp32 statistics; one warp per row.

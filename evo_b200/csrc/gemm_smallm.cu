@@ -347,12 +347,9 @@ int launch(const evo_gemm_smallm_params* p, cudaStream_t st) {
   EVO_REQUIRE(p->workspace != nullptr && p->workspace_bytes >= need, "evo_gemm_smallm: workspace too small (%zu < %zu)", p->workspace_bytes, need);
   g.counters = (int*)p->workspace;
   g.slots = (float*)((uint8_t*)p->workspace + 16384);
-  static bool attr_done = false;
+  static unsigned long long attr_done = 0;
   auto kern = gemm_smallm_kernel<EPI>;
-  if (!attr_done) {
-    EVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_done = true;
-  }
+  { int rc_ = ensure_dyn_smem(kern, 224 * 1024, attr_done); if (rc_) return rc_; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NTHREADS);
@@ -370,7 +367,9 @@ int launch(const evo_gemm_smallm_params* p, cudaStream_t st) {
 
 }  // namespace
 
+#ifdef EVO_SMALLM_TRACE   // in-kernel time stamps: experiment builds only (nvcc -DEVO_SMALLM_TRACE), not part of the shipped ABI
 extern "C" void evo_debug_smallm_trace(void* buf) { g_trace = (long long*)buf; }
+#endif
 
 extern "C" size_t evo_gemm_smallm_workspace(int64_t M, int64_t N, int64_t K, int epilogue) {
   (void)K;

@@ -307,12 +307,9 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
     if (env_r) g.raster_n = atoi(env_r);
     if (env_g) g.group_m = std::max(1, atoi(env_g));
   }
-  static bool attr_done = false;
+  static unsigned long long attr_done = 0;     // one bit per device (the template instance has its own copy)
   auto kern = gemm_tcgen05_kernel<CG, EPI, BN>;
-  if (!attr_done) {
-    EVO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
-    attr_done = true;
-  }
+  { int rc_ = ensure_dyn_smem(kern, C_::SMEM_BYTES, attr_done); if (rc_) return rc_; }
   int sms = device_sm_count();
   int n_tiles = g.m_blocks * g.n_blocks;
   cudaLaunchConfig_t cfg = {};

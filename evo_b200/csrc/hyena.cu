@@ -338,12 +338,9 @@ extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t 
     a.fir_w = (const bf16*)p->fir_w; a.fir_b = (const bf16*)p->fir_b; a.Dskip = (const bf16*)p->Dskip;
     a.poles = p->poles; a.residues = p->residues; a.halo = (const bf16*)p->halo; a.state_in = p->state_in; a.state_out = p->state_out;
     a.seg_states = (float*)workspace; a.B = p->B; a.D = p->D; a.nseg = nseg; a.L = p->L; a.seg_len = seg_len;
-    static bool attr_done = false;
-    if (!attr_done) {
-      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES)));
-      EVO_CUDA(cudaFuncSetAttribute(hyena_scan_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(STAGES)));
-      attr_done = true;
-    }
+    static unsigned long long done_s = 0, done_o = 0;
+    if ((rc = ensure_dyn_smem(hyena_scan_tma_kernel<true>, smem_bytes(STAGES), done_s))) return rc;
+    if ((rc = ensure_dyn_smem(hyena_scan_tma_kernel<false>, smem_bytes(STAGES), done_o))) return rc;
     dim3 grid(p->D / CH_PER_CTA, p->B, nseg), block(evo_hy2::THREADS);
     // ring depth 4 (96 KB): two CTAs can co-reside and hide each other's latency when the grid exceeds the SM count.
     // An 8-deep ring for single-CTA-per-SM grids was measured and did not help (1.21 vs 1.06-1.13 ms at B=8, L=8193).

@@ -34,6 +34,24 @@ def _read_safetensors(model_dir: str) -> dict:
     raise FileNotFoundError(f"No safetensors files found in {model_dir}. Expected model.safetensors.index.json or model.safetensors.")
 
 
+# the reference resolves config_path relative to its package (pkgutil.get_data, evo/models.py:141); those two names
+# map to the built-in dicts of evo_b200/configs.py, which hold the same keys and values
+_PACKAGE_CONFIGS = {"evo-1-8k-base_inference.yml": "evo-1-8k-base", "evo-1-131k-base_inference.yml": "evo-1-131k-base"}
+
+
+def _resolve_config(model_name: str, config_path: Optional[str]) -> dict:
+    if config_path is None:
+        return get_config(model_name)
+    if os.path.isfile(config_path):
+        with open(config_path) as f:
+            return yaml.safe_load(f)
+    base = os.path.basename(config_path)
+    if base in _PACKAGE_CONFIGS and os.path.dirname(config_path) in ("configs", "evo/configs"):
+        return get_config(_PACKAGE_CONFIGS[base])
+    raise FileNotFoundError(f"config file {config_path!r} does not exist (and is not one of the package configs "
+                            f"{sorted('configs/' + k for k in _PACKAGE_CONFIGS)})")
+
+
 def load_checkpoint(model_name: str = "evo-1-8k-base", config_path: Optional[str] = None, device: str = None,
                     model_dir: Optional[str] = None, random_init: bool = False, seed: int = 0, *args, **kwargs):
     """HF snapshot -> safetensors -> StripedHyena on `device`.
@@ -41,12 +59,7 @@ def load_checkpoint(model_name: str = "evo-1-8k-base", config_path: Optional[str
     model_dir: use an already-downloaded snapshot directory instead of huggingface_hub.
     random_init: skip the checkpoint (benchmarks / tests on boxes without network) and keep the
     constructor's random initialisation, seeded."""
-    if config_path is not None and os.path.exists(config_path):
-        with open(config_path) as f:
-            cfg = yaml.safe_load(f)
-    else:
-        cfg = get_config(model_name)
-    cfg = dotdict(cfg)
+    cfg = dotdict(_resolve_config(model_name, config_path))
 
     if random_init:
         # build straight on the target device: no 26 GB fp32 host copy of a 7B model

@@ -117,15 +117,23 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
     pc = None
     if transport in ("auto", "peer") and world > 1:
         pc = getattr(model, "_peer_carry", None)
-        if pc is None or pc.key != (world, rank, B, d, S, str(dev)):
+        if pc is None or (pc is not False and pc.key != (world, rank, B, d, S, str(dev))):
             try:
                 pc = PeerCarry(world, rank, B, d, S, dev, group)
             except Exception as ex:  # symmetric memory unavailable on this system
-                if transport == "peer":
-                    raise
                 pc = None
                 model._peer_carry_error = repr(ex)
-            model._peer_carry = pc
+            # the transport is a collective decision: one rank on NCCL all-gathers while the others spin on peer flags would
+            # hang, so every rank learns whether ALL of them have the peer path
+            ok = torch.tensor([1 if pc is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                if transport == "peer":
+                    raise _lib.EvoError("peer-memory transport unavailable on at least one rank: " + str(getattr(model, "_peer_carry_error", "")))
+                pc = None
+            model._peer_carry = pc if pc is not None else False     # False = decided: NCCL (do not retry every forward)
+        if pc is False:
+            pc = None
         if pc is not None:
             dist.barrier(group)          # nobody is still reading ring slots of the previous forward
     since_sync = 0

@@ -220,8 +220,17 @@ class StripedHyena(nn.Module):
             packed[i] = {"w12": w12, "w3": w3, "ipad": ipad}
         hd = self.config.hidden_size // self.config.num_attention_heads
         base = self.config.get("rotary_emb_base") or 10000
-        # flash_attn recomputes inv_freq in fp32 when the buffer is not fp32 (layers/rotary.py:386-401)
-        packed["inv_freq"] = (1.0 / (base ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))).to(dev)
+        # flash_attn keeps the checkpoint's inv_freq buffer when it is fp32 and recomputes it in fp32 otherwise
+        # (layers/rotary.py:386-401); one table per model: every attention block must then agree
+        analytic = (1.0 / (base ** (torch.arange(0, hd, 2, dtype=torch.float32) / hd))).to(dev)
+        bufs = [self.blocks[i].inner_mha_cls.rotary_emb.inv_freq for i in sorted(self._attn_idxs)]
+        if bufs and bufs[0].dtype == torch.float32:
+            for b_ in bufs[1:]:
+                if b_.dtype != torch.float32 or not torch.equal(b_, bufs[0]):
+                    raise _lib.EvoError("attention blocks carry different rotary inv_freq buffers; one rope table per model is supported")
+            packed["inv_freq"] = bufs[0].detach().to(dev).contiguous()
+        else:
+            packed["inv_freq"] = analytic
         self._packed = packed
         return packed
 
@@ -255,6 +264,7 @@ class StripedHyena(nn.Module):
         need = lib.evo_gemm_smallm_workspace(M, N, K, epi)
         ws = self._smallm_ws
         if ws is None or ws.numel() < need or ws.device != a.device:
+            self._decode = None      # a captured decode graph holds the old workspace address
             ws = self._smallm_ws = torch.zeros(max(need, lib.evo_gemm_smallm_workspace(M, 256, 64, EPI_GELU_GATE)), dtype=torch.uint8, device=a.device)
         n_out = N // 2 if epi == EPI_GELU_GATE else N
         p = GemmSmallMParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=n_out,
@@ -276,6 +286,7 @@ class StripedHyena(nn.Module):
             sin = torch.empty_like(cos)
             check(_lib.lib().evo_rope_tables(ptr(cos), ptr(sin), ptr(self._packed["inv_freq"]), 0, n, hd2, scaling, self._stream()), "evo_rope_tables")
             self._rope = (cos, sin)
+            self._decode = None      # a captured decode graph holds the old tables' addresses
         return self._rope
 
     def _mlp_residual(self, i, blk, u, M):
@@ -544,7 +555,9 @@ class StripedHyena(nn.Module):
                 hy_ip.fir_state_dict[i] = hy_ip.fir_state_dict[i].contiguous()
         key = (B, x.dtype, tuple(hy_ip.state_dict[i].data_ptr() for i in sorted(hy_ip.state_dict)),
                tuple(hy_ip.fir_state_dict[i].data_ptr() for i in sorted(hy_ip.fir_state_dict)),
-               tuple(mha_ip.key_value_memory_dict[i].data_ptr() for i in sorted(mha_ip.key_value_memory_dict)))
+               tuple((mha_ip.key_value_memory_dict[i].data_ptr(), mha_ip.key_value_memory_dict[i].shape[1]) for i in sorted(mha_ip.key_value_memory_dict)),
+               # every other address the captured launches bake in: rope tables, stream-K workspace
+               tuple(t.data_ptr() for t in (self._rope or ())), self._smallm_ws.data_ptr() if self._smallm_ws is not None else 0)
         off = int(mha_ip.seqlen_offset)
         for i in mha_ip.key_value_memory_dict:
             if off >= mha_ip.key_value_memory_dict[i].shape[1]:

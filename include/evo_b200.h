@@ -93,10 +93,6 @@ int evo_gemm_smallm(const evo_gemm_smallm_params* p, void* stream);
  * the GEMM tail in front of it).  Every decode-step kernel begins with griddepcontrol.launch_dependents and waits
  * (griddepcontrol.wait) before it first touches dependent data.  Process-wide switch; returns the previous value. */
 int evo_set_pdl(int level);
-/* debug hook: device buffer of gridDim.x * 16 int64 time stamps written by evo_gemm_smallm (NULL = off) */
-void evo_debug_smallm_trace(void* buf);
-/* test comparator only (cuBLASLt, plain C = A.W^T [+bias]); never on the product path */
-int evo_gemm_cublaslt_reference(const evo_gemm_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- fused Hyena operator: HyenaInferenceEngine.parallel_fir + ParallelHyenaFilter.
  * compute_filter + parallel_iir (+ prefill_via_modal_fft) of stripedhyena 0.2.2, as one
@@ -172,8 +168,6 @@ typedef struct {
  * variant 2: ping-pong kernel: two query tiles per CTA, P kept in TMEM (A operand from TMEM), V in place. */
 size_t evo_attn_fwd_workspace(const evo_attn_params* p, int variant);
 int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* workspace, size_t workspace_bytes, void* stream);
-/* plain CUDA-core comparator for tests; never on the product path */
-int evo_attn_fwd_simple(const evo_attn_params* p, void* stream);
 
 /* append k,v of qkv (B, L, 3, H, hd) at rows [pos0, pos0+L) of the KV cache
  * (max_B, max_seqlen, 2, H, hd) bf16 — MHA._update_kv_cache (mha.py:344-370). */
@@ -195,8 +189,8 @@ int evo_decode_attn(const void* qkv, const void* cache, void* out, const int64_t
                     int64_t max_seqlen, int nsplit, float softmax_scale, void* workspace, size_t workspace_bytes, void* stream);
 int evo_advance_position(int64_t* pos, int64_t delta, void* stream);
 
-/* ---- elementwise glue kept for completeness / tests ---- */
-int evo_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* (test comparators -- cuBLASLt GEMM, CUDA-core attention, bf16 add -- live in tests/support/libevo_b200_test.so,
+ *  not in this library) */
 
 /* ---- scoring epilogue: evo/scoring.py:36-59 logits_to_logprobs ----
  * logits (rows, V) bf16; targets (rows) int64 (-1 = skip -> 0); out (rows) fp32 =

@@ -265,7 +265,8 @@ def _attn(qkv, B, L, H, variant, simple=False, cache=None, off=0):
         ap.k, ap.v, ap.kv_tok_stride, ap.kv_batch_stride, ap.Lk = cache.data_ptr(), cache.data_ptr() + 2 * d, 2 * d, cache.shape[1] * 2 * d, off + L
     lib = _lib.lib()
     if simple:
-        _lib.check(lib.evo_attn_fwd_simple(C.byref(ap), stream()), "attn_simple")
+        from tests import support as TS
+        TS.check(TS.lib().evot_attn_fwd_simple(C.byref(ap), stream()), "attn_simple")
     else:
         n = lib.evo_attn_fwd_workspace(C.byref(ap), variant)
         ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
@@ -347,7 +348,8 @@ def stage_perf_gemm():
                 rec[f"tcgen05_v{variant}_err"] = str(e)[:200]
         out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
         p = _lib.GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=N, bias=bias.data_ptr(), residual=None, ldr=N, M=M, N=N, K=K, epilogue=1, variant=0)
-        fn = lambda: _lib.check(_lib.lib().evo_gemm_cublaslt_reference(C.byref(p), _lib.ptr(ws), ws.numel(), stream()))
+        from tests import support as TS
+        fn = lambda: TS.check(TS.lib().evot_gemm_cublaslt(C.byref(p), _lib.ptr(ws), ws.numel(), stream()))
         ms = timeit(fn); rec["cublaslt_ms"] = ms; rec["cublaslt_tflops"] = flops / ms / 1e9
         ms = timeit(lambda: torch.matmul(a, w.T)); rec["torch_ms"] = ms; rec["torch_tflops"] = flops / ms / 1e9
         emit("perf_gemm", **rec)

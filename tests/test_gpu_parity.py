@@ -362,7 +362,8 @@ def test_gemm_full_size_against_cublaslt():
     ref = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
     ws = torch.empty(64 << 20, dtype=torch.uint8, device=DEV)
     p = _lib.GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=ref.data_ptr(), ldc=N, bias=bias.data_ptr(), residual=None, ldr=N, M=M, N=N, K=K, epilogue=1, variant=0)
-    _lib.check(_lib.lib().evo_gemm_cublaslt_reference(C.byref(p), _lib.ptr(ws), ws.numel(), stream()))
+    from tests import support as TS
+    TS.check(TS.lib().evot_gemm_cublaslt(C.byref(p), _lib.ptr(ws), ws.numel(), stream()), "cublaslt comparator")
     torch.cuda.synchronize()
     d = (out.float() - ref.float()).abs()
     assert d.max().item() <= 2 * BF16_EPS * ref.float().abs().max().item()

@@ -307,3 +307,19 @@ def test_generate_function_batches_equal_lengths_and_scores_like_the_reference(c
     # ragged prompts: falls back to one at a time and says why
     evo_b200.generate(["ACGT", "TT"], _OracleAsModel(cfg, sd), tok, n_tokens=2, top_k=1, cached_generation=False, verbose=1, device="cpu")
     assert "different lengths" in capsys.readouterr().err
+
+
+def test_config_path_resolution_matches_the_reference(tmp_path):
+    """evo/models.py:141 loads config_path relative to the package, or fails; a typo must not silently run the default geometry."""
+    from evo_b200.models import _resolve_config
+    from evo_b200.configs import get_config
+    assert _resolve_config("evo-1-8k-base", None) == get_config("evo-1-8k-base")
+    assert _resolve_config("evo-1-131k-base", "configs/evo-1-131k-base_inference.yml")["rotary_emb_scaling_factor"] == 16
+    assert "rotary_emb_scaling_factor" not in _resolve_config("evo-1-8k-base", "configs/evo-1-8k-base_inference.yml")
+    p = tmp_path / "custom.yml"
+    p.write_text("hidden_size: 64\n")
+    assert _resolve_config("evo-1-8k-base", str(p)) == {"hidden_size": 64}
+    with pytest.raises(FileNotFoundError):
+        _resolve_config("evo-1-8k-base", str(tmp_path / "typo.yml"))
+    with pytest.raises(FileNotFoundError):
+        _resolve_config("evo-1-8k-base", "elsewhere/evo-1-8k-base_inference.yml")

@@ -93,11 +93,16 @@ def main():
             for i in range(3):
                 launch(i)
             torch.cuda.synchronize()
-            lib.evo_debug_smallm_trace(_lib.ptr(tr))
+            import ctypes
+            raw = ctypes.CDLL(_lib.LIB_PATH)
+            if not hasattr(raw, "evo_debug_smallm_trace"):
+                raise SystemExit("--trace needs a library built with NVCC_EXTRA=-DEVO_SMALLM_TRACE (the hook is not in the shipped ABI)")
+            raw.evo_debug_smallm_trace.argtypes = [ctypes.c_void_p]
+            raw.evo_debug_smallm_trace(_lib.ptr(tr))
             tr.zero_()
             launch(3)
             torch.cuda.synchronize()
-            lib.evo_debug_smallm_trace(None)
+            raw.evo_debug_smallm_trace(None)
             t = tr.view(148, 16).cpu().double()
             t = t[t[:, 0] > 0]
             ghz = ((t[:, 8] - t[:, 1]) / (t[:, 15] - t[:, 0]).clamp(min=1)).median().item()      # SM cycles per ns
