@@ -170,6 +170,165 @@ def bench_reference(args, wl):
     }))
 
 
+def _dist_ctx():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(f"cuda:{local}")
+    return world, rank, local
+
+
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(x, world, dev):
+    """(max over ranks, per-rank list) of a python float; device-side all-gather."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return x, [x]
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    allt = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    vals = [float(v.item()) for v in allt]
+    return max(vals), vals
+
+
+def time_steps(fwd, steps, world, dev):
+    """EXACTLY `steps` calls of fwd, CUDA events on the launch stream, barrier + synchronize on both sides.
+    No per-kernel instrumentation runs inside this region."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(world)
+    e0.record()
+    for _ in range(steps):
+        fwd()
+    e1.record()
+    _barrier(world)
+    return _max_over_ranks(e0.elapsed_time(e1), world, dev)
+
+
+def kernel_breakdown(model, fwd, n, world):
+    """Separate pass (outside the timed region): per-kernel CUDA events -> {kind: [work, ms, launches]} per step, and the pass's own ms/step."""
+    import torch
+    _barrier(world)
+    model._prof = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fwd()
+    e1.record()
+    _barrier(world)
+    prof, model._prof = model._prof, None
+    by = {}
+    for kind, work, a, b in prof:
+        key = kind if kind.startswith("comm/") else kind.split("/")[0]
+        d = by.setdefault(key, [0.0, 0.0, 0])
+        d[0] += work / n; d[1] += a.elapsed_time(b) / n; d[2] += 1.0 / n
+    return by, e0.elapsed_time(e1) / n
+
+
+def rooflines(by, step_ms, workload, peaks):
+    roof = {}
+    if "gemm" in by:
+        ach = by["gemm"][0] / (by["gemm"][1] / 1e3) / 1e12
+        roof["roofline"] = {"kernel": "gemm_tcgen05_kernel (all linear layers)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                            "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic("gemm_tcgen05", workload),
+                            "algorithmic_flops_per_launch": by["gemm"][0] / by["gemm"][2],
+                            "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "share_of_step": by["gemm"][1] / step_ms, "launches_per_step": by["gemm"][2]}
+    if "hyena" in by:
+        ach = by["hyena"][0] / (by["hyena"][1] / 1e3) / 1e9
+        roof["roofline_hyena"] = {"kernel": "hyena_scan_ms_kernel (fused FIR + gate + modal long conv + gate)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
+                                  "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic("hyena_scan", workload),
+                                  "algorithmic_bytes_per_launch": by["hyena"][0] / by["hyena"][2], "peak_source": peaks["source"],
+                                  "share_of_step": by["hyena"][1] / step_ms, "launches_per_step": by["hyena"][2]}
+    if "attn" in by:
+        ach = by["attn"][0] / (by["attn"][1] / 1e3) / 1e12
+        roof["roofline_attn"] = {"kernel": "attn_pp_kernel (tcgen05 causal attention)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                                 "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic("attn_", workload),
+                                 "share_of_step": by["attn"][1] / step_ms, "launches_per_step": by["attn"][2]}
+    return roof
+
+
+def variant_of(model, model_name):
+    """A second StripedHyena that SHARES every parameter and packed weight of `model` under another config (the Evo
+    checkpoints have one geometry; evo-1-131k-base only adds the rotary interpolation, evo/configs/evo-1-131k-base_inference.yml:39-40)."""
+    import copy
+    from evo_b200.configs import get_config
+    from evo_b200.stripedhyena import dotdict
+    model._ensure_packed()
+    m = copy.copy(model)
+    m.config = dotdict(get_config(model_name))
+    m._rope, m._decode, m._prof = None, None, None
+    if hasattr(m, "_peer_carry"):
+        del m._peer_carry
+    return m
+
+
+def sp131k_record(model8k, world, rank, dev, steps, warmup, peaks):
+    """BASELINE.json configs[2]: evo-1-131k-base, batch 1 x 131072 nt, the sequence sharded over the `world` GPUs of the
+    box (strong scaling; world == 1: the plain single-GPU forward).  Timed like the main line; afterwards, outside the
+    timed region, one instrumented step names where the time went (kernels and every communication piece) and every
+    rank compares its shard of the logits with the UNSHARDED single-GPU forward of the same ids."""
+    import torch
+    import torch.distributed as dist
+    from evo_b200 import CharLevelTokenizer, prepare_batch
+    wl = WORKLOADS["131k"]
+    model = variant_of(model8k, wl["model"])
+    tok = CharLevelTokenizer(512)
+    seqs = synthetic_seqs(wl["batch"], wl["nt"], seed=1234)                 # same ids on every rank
+    ids_full, _ = prepare_batch(seqs, tok, prepend_bos=False, device=dev)
+    L = ids_full.shape[1]
+    if world > 1:
+        from evo_b200.parallel import sequence_parallel_forward
+        shard = L // world
+        ids = ids_full[:, rank * shard:(rank + 1) * shard].contiguous()
+        fwd = lambda: sequence_parallel_forward(model, ids, rank, world)
+    else:
+        shard = L
+        fwd = lambda: model(ids_full)[0]
+    for _ in range(warmup):
+        fwd()
+    ms, per_rank = time_steps(fwd, steps, world, dev)
+    by, prof_ms = kernel_breakdown(model, fwd, 1, world)
+    rec = {"workload": wl["desc"], "value": wl["batch"] * wl["nt"] * steps / (ms / 1e3), "unit": "nt/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "parallelism": f"sp{world}", "scaling": "strong", "per_rank_ms_per_step": [v / steps for v in per_rank], "tokens_per_rank": shard}
+    if world > 1:
+        tr = getattr(model, "_peer_carry", None)
+        rec["hyena_carry_transport"] = "nvlink peer stores + flags (own kernels)" if tr not in (None, False) else "nccl all-gather"
+    # rank 0's instrumented step: kernels and communication, each as ms per step; what no event covered is host-side gaps
+    comm = {k.split("/", 1)[1]: v[1] for k, v in by.items() if k.startswith("comm/")}
+    kern = {k: v[1] for k, v in by.items() if not k.startswith("comm/")}
+    rec["comm_ms"] = {**comm, "total": sum(comm.values())}
+    rec["kernel_ms"] = kern
+    rec["instrumented_step_ms"] = prof_ms
+    rec["unattributed_ms"] = prof_ms - sum(comm.values()) - sum(kern.values())
+    rec.update(rooflines(by, prof_ms, "131k", peaks))
+    if world > 1:
+        # correctness of the sharded forward on THIS run: my shard vs the unsharded forward of the same ids on my GPU
+        mine = fwd()
+        ref = model(ids_full)[0][:, rank * shard:(rank + 1) * shard]
+        d = (mine.float() - ref.float()).abs()
+        stats = [d.max().item(), d.mean().item(), (mine.argmax(-1) == ref.argmax(-1)).float().mean().item(), ref.float().abs().max().item(),
+                 float(torch.isfinite(mine.float()).all().item())]
+        del mine, ref, d
+        allst = [None] * world
+        dist.all_gather_object(allst, stats)
+        rec["sp_check"] = {"reference": "unsharded forward of the same ids on each rank's own GPU",
+                           "per_rank": [{"max_abs": s[0], "mean_abs": s[1], "argmax_agree": s[2], "ref_abs_max": s[3], "finite": bool(s[4])} for s in allst]}
+    torch.cuda.empty_cache()
+    return rec
+
+
 def bench_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -177,13 +336,8 @@ def bench_ours(args, wl):
     from evo_b200 import _lib, CharLevelTokenizer, prepare_batch, score_sequences
     from evo_b200.models import load_checkpoint
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    world, rank, local = _dist_ctx()
     dev = f"cuda:{local}"
-    torch.cuda.set_device(dev)
     steps = args.steps if args.steps is not None else 5
     warmup = args.warmup if args.warmup is not None else 3
 
@@ -193,7 +347,7 @@ def bench_ours(args, wl):
     seqpar = args.workload == "131k" and world > 1
     if seqpar:
         from evo_b200.parallel import sequence_parallel_forward
-        ids_full, _ = prepare_batch(seqs, tok, prepend_bos=False, device=dev)
+        ids_full, _ = prepare_batch(synthetic_seqs(wl["batch"], wl["nt"], seed=0), tok, prepend_bos=False, device=dev)
         shard = ids_full.shape[1] // world
         ids = ids_full[:, rank * shard:(rank + 1) * shard].contiguous()
         fwd = lambda: sequence_parallel_forward(model, ids, rank, world)
@@ -203,88 +357,63 @@ def bench_ours(args, wl):
         fwd = lambda: model(ids)
         tokens_per_step_job = wl["batch"] * wl["nt"] * world
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(warmup):
         fwd()
-    barrier()
+    _barrier(world)
 
-    # ---- timed region 1: device-resident inputs, per-kernel events for the roofline
+    # ---- timed region 1: device-resident inputs, nothing but the forward inside
     lib = _lib.lib()
-    model._prof = []
     lib.evo_reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(steps):
-            fwd()
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
+        ms, per_rank_ms = time_steps(fwd, steps, world, dev)
     launches = lib.evo_launch_count()
-    prof, model._prof = model._prof, None
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
     value = tokens_per_step_job * steps / (ms / 1e3)
+
+    # ---- separate pass: per-kernel events for the rooflines (not part of `value`)
+    by, prof_ms = kernel_breakdown(model, fwd, 2, world)
 
     # ---- timed region 2: end to end through the public API with host inputs
     e2e = None
     if not seqpar:
         for _ in range(2):
             score_sequences(seqs, model, tok, device=dev)
-        barrier()
+        _barrier(world)
         t0 = time.perf_counter()
         for _ in range(steps):
             scores = score_sequences(seqs, model, tok, device=dev)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = t.item()
+        dt, _ = _max_over_ranks(time.perf_counter() - t0, world, dev)
         L1 = wl["nt"] + 1
         e2e = {"value": tokens_per_step_job * steps / dt, "unit": "nt/s",
                "h2d_bytes_per_step": wl["batch"] * L1 * 8, "d2h_bytes_per_step": wl["batch"] * wl["nt"] * 4,
                "api": "evo_b200.score_sequences(list[str]) -> list[float]"}
 
+    peaks = measured_peaks()
+    sub = {}
+    if args.workload == "8k" and not args.no_sub:
+        # BASELINE.json configs[2] next to the headline, at every N
+        try:
+            sub["sp131k"] = sp131k_record(model, world, rank, dev, steps=args.sub_steps, warmup=1, peaks=peaks)
+        except Exception as ex:  # noqa  (a failed sub-record must not cost the headline line)
+            sub["sp131k"] = {"error": repr(ex)[:300]}
+        if world == 1 and not args.no_gen:
+            try:
+                sub["gen"] = generate_record(model, dev, peaks)
+            except Exception as ex:  # noqa
+                sub["gen"] = {"error": repr(ex)[:300]}
+
     if rank == 0:
-        peaks = measured_peaks()
-        by = {}
-        for kind, work, a, b in prof:
-            d = by.setdefault(kind.split("/")[0], [0.0, 0.0, 0])
-            d[0] += work; d[1] += a.elapsed_time(b); d[2] += 1
-        roof = {}
-        if "gemm" in by:
-            ach = by["gemm"][0] / (by["gemm"][1] / 1e3) / 1e12
-            roof["roofline"] = {"kernel": "gemm_tcgen05_kernel (all linear layers)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                                "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic("gemm_tcgen05", args.workload),
-                                "algorithmic_flops_per_launch": by["gemm"][0] / by["gemm"][2],
-                                "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "share_of_step": by["gemm"][1] / ms, "launches_per_step": by["gemm"][2] / steps}
-        if "hyena" in by:
-            ach = by["hyena"][0] / (by["hyena"][1] / 1e3) / 1e9
-            roof["roofline_hyena"] = {"kernel": "hyena_scan_tma_kernel (fused FIR + gate + modal long conv + gate)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"],
-                                      "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": ncu_traffic("hyena_scan", args.workload),
-                                      "algorithmic_bytes_per_launch": by["hyena"][0] / by["hyena"][2], "peak_source": peaks["source"],
-                                      "share_of_step": by["hyena"][1] / ms, "launches_per_step": by["hyena"][2] / steps}
-        if "attn" in by:
-            ach = by["attn"][0] / (by["attn"][1] / 1e3) / 1e12
-            roof["roofline_attn"] = {"kernel": "attn_fwd_kernel (tcgen05 causal attention)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
-                                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], "traffic": ncu_traffic("attn_fwd", args.workload),
-                                     "share_of_step": by["attn"][1] / ms, "launches_per_step": by["attn"][2] / steps}
+        roof = rooflines(by, prof_ms, args.workload, peaks)
         out = {
             "metric": "nucleotides/sec forward, evo-1 7B", "value": value, "unit": "nt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if seqpar else "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic uniform ACGT (np.random.default_rng), random-init weights of the 7B architecture",
             "config": {"workload": wl["desc"], "global_batch": wl["batch"] * (1 if seqpar else world), "seq_len": wl["nt"] + (0 if seqpar else 1),
                        "parallelism": (f"sp{world}" if seqpar else f"replicas x{world}"),
-                       "l2": "inputs >> L2: every step streams 12.9 GB of weights and 0.5-1.6 GB activation tensors (L2 = 126 MB)"},
-            "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e, **roof,
+                       "l2": "inputs >> L2: every step streams 12.9 GB of weights and 0.5-1.6 GB activation tensors (L2 = 126 MB)",
+                       "timing": "value: CUDA events around exactly `steps` forwards, no per-kernel events inside; rooflines from a separate instrumented pass"},
+            "per_rank_ms_per_step": [v / steps for v in per_rank_ms],
+            "clocks": clocks.summary(), "gpu_launches": int(launches), "e2e": e2e, **roof, **sub,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -297,95 +426,96 @@ def bench_ours(args, wl):
         dist.destroy_process_group()
 
 
-def bench_generate(args, wl):
-    """Secondary workload: the L == 1 step path (recurrent Hyena state + KV cache) after a 4096-nt prefill.
-    value = generated nt/s with the state resident on the GPU (greedy token fed back on the device);
-    e2e = evo_b200.generate() from prompt strings to generated strings (prefill included).  Rank-local (replicas)."""
+def generate_record(model, dev, peaks, steps=64, warmup=4, n_new=None, world=1, rank=0):
+    """BASELINE.json configs[3]: cached generation, batch 16, prompt 4096 nt, greedy.  One step = one new nucleotide per
+    sequence through the L == 1 path (recurrent Hyena state + KV cache).
+    value = generated nt/s with the state resident on the GPU; e2e = evo_b200.generate() from prompt strings to generated
+    strings, the 4096-nt prefill and `n_new` decode steps included."""
     import torch
     import evo_b200
     from evo_b200 import _lib, CharLevelTokenizer
-    from evo_b200.models import load_checkpoint
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    dev = f"cuda:{local}"
-    torch.cuda.set_device(dev)
-    steps = args.steps if args.steps is not None else 64
-    warmup = max(3, args.warmup if args.warmup is not None else 4)
-    model = load_checkpoint(wl["model"], device=dev, random_init=True, seed=0)
+    wl = WORKLOADS["gen"]
     tok = CharLevelTokenizer(512)
     B, P = wl["batch"], wl["nt"]
+    n_new = n_new if n_new is not None else P          # configs[3]: prefill 4096 + decode 4096
     seqs = synthetic_seqs(B, P, seed=rank)
     ids = torch.tensor([tok.tokenize(s) for s in seqs], dtype=torch.long, device=dev)
     d = model.initialize_inference_params()
     d["mha"].max_batch_size = d["hyena"].max_batch_size = B
     logits, d = model(ids, inference_params_dict=d)
     d["mha"].seqlen_offset = d["hyena"].seqlen_offset = P
-    nxt = logits[:, -1].argmax(-1, keepdim=True)
+    state = {"nxt": logits[:, -1].argmax(-1, keepdim=True), "d": d}
 
     def step():
-        nonlocal nxt, d
-        lg, d = model(nxt, inference_params_dict=d)
-        nxt = lg[:, -1].argmax(-1, keepdim=True)
-        d["mha"].seqlen_offset += 1
-        d["hyena"].seqlen_offset += 1
+        lg, state["d"] = model(state["nxt"], inference_params_dict=state["d"])
+        state["nxt"] = lg[:, -1].argmax(-1, keepdim=True)
+        state["d"]["mha"].seqlen_offset += 1
+        state["d"]["hyena"].seqlen_offset += 1
 
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     lib = _lib.lib()
-    lib.evo_reset_launch_count()
+    n0 = lib.evo_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    launches = lib.evo_launch_count()
+    launches = lib.evo_launch_count() - n0
     if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    value = B * world * steps / (ms / 1e3)
-    # end to end: prompts as strings -> generated strings, through the reference-shaped API (prefill + n_tokens steps)
-    n_new = 32
-    del d
+        ms, _ = _max_over_ranks(ms, world, dev)
+    del state, d, logits
     torch.cuda.empty_cache()
+    # end to end: prompts as strings -> generated strings through the reference-shaped API (prefill + n_new steps)
     evo_b200.generate(seqs, model, tok, n_tokens=4, top_k=1, cached_generation=True, verbose=0, device=dev, force_prompt_threshold=P)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    out, _ = evo_b200.generate(seqs, model, tok, n_tokens=n_new, top_k=1, cached_generation=True, verbose=0, device=dev, force_prompt_threshold=P)
+    evo_b200.generate(seqs, model, tok, n_tokens=n_new, top_k=1, cached_generation=True, verbose=0, device=dev, force_prompt_threshold=P)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    cfg = model.config
+    n_attn = len(cfg.attn_layer_idxs)
+    weight_bytes = sum(p.numel() * p.element_size() for p in model.parameters())
+    ctx = P + warmup + steps / 2.0
+    kv_bytes = n_attn * B * ctx * 2 * cfg.hidden_size * 2
+    ach = (weight_bytes + kv_bytes) / (ms / steps / 1e3) / 1e9
+    torch.cuda.empty_cache()
+    return {
+        "metric": "generated nucleotides/sec, evo-1.5 7B cached decode", "workload": wl["desc"], "value": B * world * steps / (ms / 1e3), "unit": "nt/s",
+        "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "gpu_launches": int(launches),
+        "decode": {"streamk": model.decode_streamk, "pdl": model.decode_pdl, "cuda_graph": model.decode_graph},
+        "e2e": {"value": B * world * n_new / dt, "unit": "nt/s", "seconds": dt, "new_tokens": n_new, "h2d_bytes": B * P * 8, "d2h_bytes": B * n_new * (8 + 512 * 4),
+                "api": f"evo_b200.generate(prompts, n_tokens={n_new}, top_k=1, cached_generation=True, force_prompt_threshold={P}): {P}-nt prefill + {n_new} steps, strings in / strings out"},
+        "roofline": {"kernel": "decode step (gemm_smallm_kernel weight stream + decode_attn_tma_kernel KV stream)", "bound": "hbm", "achieved": ach,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                     "algorithmic_bytes_per_step": weight_bytes + kv_bytes, "peak_source": peaks["source"]},
+    }
+
+
+def bench_generate(args, wl):
+    """`--workload gen`: the generation record as its own bench line (replicas when N > 1)."""
+    import torch
+    import torch.distributed as dist
+    from evo_b200.models import load_checkpoint
+    world, rank, local = _dist_ctx()
+    dev = f"cuda:{local}"
+    steps = args.steps if args.steps is not None else 64
+    warmup = max(3, args.warmup if args.warmup is not None else 4)
+    model = load_checkpoint(wl["model"], device=dev, random_init=True, seed=0)
+    with ClockSampler(local) as clocks:
+        rec = generate_record(model, dev, measured_peaks(), steps=steps, warmup=warmup, n_new=args.gen_tokens, world=world, rank=rank)
     if rank == 0:
-        peaks = measured_peaks()
-        cfg = model.config
-        n_attn = len(cfg.attn_layer_idxs)
-        weight_bytes = sum(p.numel() * p.element_size() for p in model.parameters())
-        ctx = P + warmup + steps / 2.0
-        kv_bytes = n_attn * B * ctx * 2 * cfg.hidden_size * 2
-        ach = (weight_bytes + kv_bytes) / (ms / steps / 1e3) / 1e9
-        print(json.dumps({
-            "metric": "generated nucleotides/sec, evo-1.5 7B cached decode", "value": value, "unit": "nt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic uniform ACGT prompts, random-init weights of the 7B architecture",
-            "config": {"workload": wl["desc"], "global_batch": B * world, "seq_len": P, "parallelism": f"replicas x{world}",
-                       "l2": "every step streams 12.9 GB of weights and ~3.2 GB of KV cache (L2 = 126 MB)",
-                       "decode": {"streamk": model.decode_streamk, "pdl": model.decode_pdl, "cuda_graph": model.decode_graph}},
-            "clocks": clocks.summary(), "gpu_launches": int(launches),
-            "e2e": {"value": B * world * n_new / dt, "unit": "nt/s", "h2d_bytes_per_step": B * P * 8 // n_new, "d2h_bytes_per_step": B * 4,
-                    "api": f"evo_b200.generate(prompts, n_tokens={n_new}, top_k=1, cached_generation=True): 4096-nt prefill + {n_new} steps, strings in / strings out"},
-            "roofline": {"kernel": "decode step (gemm_smallm_kernel weight stream + decode_attn_tma_kernel KV stream)", "bound": "hbm", "achieved": ach,
-                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
-                         "algorithmic_bytes_per_step": weight_bytes + kv_bytes, "peak_source": peaks["source"]},
-        }))
+        out = {"metric": rec.pop("metric"), "value": rec.pop("value"), "unit": rec.pop("unit"), "n_gpus": world, "steps": steps, "warmup": warmup,
+               "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+               "data": "synthetic uniform ACGT prompts, random-init weights of the 7B architecture",
+               "config": {"workload": rec.pop("workload"), "global_batch": wl["batch"] * world, "seq_len": wl["nt"], "parallelism": f"replicas x{world}",
+                          "l2": "every step streams 12.9 GB of weights and ~3.2 GB of KV cache (L2 = 126 MB)", "decode": rec.pop("decode")},
+               "clocks": clocks.summary(), **rec}
+        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -399,6 +529,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="8k", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="default workload only: skip the sp131k / gen sub-records")
+    ap.add_argument("--no-gen", action="store_true", help="skip the cached-generation sub-record")
+    ap.add_argument("--sub-steps", type=int, default=3, help="timed steps of the 131k sub-record")
+    ap.add_argument("--gen-tokens", type=int, default=None, help="new tokens of the end-to-end generate() run (default: 4096 = BASELINE configs[3])")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -46,6 +46,19 @@ class AttnParams(C.Structure):
                 ("q_pos0", C.c_int64), ("softmax_scale", C.c_float)]
 
 
+class ScoreParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("W", C.c_void_p), ("targets", C.c_void_p), ("logprobs", C.c_void_p), ("entropy", C.c_void_p),
+                ("M", C.c_int64), ("V", C.c_int), ("K", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class LoopParams(C.Structure):
+    _fields_ = [("forced", C.c_void_p), ("n_forced", C.c_int64), ("forced_stride", C.c_int64),
+                ("picked", C.c_void_p), ("picked_stride", C.c_int64),
+                ("kept_logits", C.c_void_p), ("n_out", C.c_int64),
+                ("top_k", C.c_int32), ("top_p", C.c_float), ("temperature", C.c_float),
+                ("seed", C.c_uint64), ("step0", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/evo_b200.h declares
 SIGNATURES = {
     "evo_last_error": (C.c_char_p, []),
@@ -75,6 +88,11 @@ SIGNATURES = {
     "evo_decode_attn_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "evo_decode_attn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "evo_advance_position": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "evo_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "evo_sample_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "evo_advance_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "evo_unembed_score_workspace": (C.c_size_t, [C.c_int64, C.c_int]),
+    "evo_unembed_score": (C.c_int, [C.POINTER(ScoreParams), C.c_void_p]),
     "evo_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
 }
 

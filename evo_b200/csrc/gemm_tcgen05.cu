@@ -57,8 +57,12 @@ struct GemmArgs {
   int m_blocks, n_blocks, group_m;
   int b_tiled;           // small-M tile only: W is tile-major [N/64][K/64][64][64] (contiguous 8 KB tiles: every DRAM page opened is fully used)
   int a_rows, n_stages, ksub;  // small-M tile only: rows of A staged per k-block, ring depth, 64-column k-blocks per ring stage
+  const long long* targets;   // EPI_LSE only: (M) target token per row (-1: none)
+  float4* part;               // EPI_LSE only: (M, n_blocks) per-row partial statistics {max, sum e^(x-max), sum e^(x-max) x, target logit}
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
+
+constexpr int EPI_LSE = 5;     // internal: scoring epilogue (evo_unembed_score); no C is written
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -233,7 +237,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
-      if constexpr (EPI == EVO_EPI_GELU_GATE && BN == BN_BIG) {
+      if constexpr (EPI == EPI_LSE) {
+        // scoring epilogue: the 256 logits of this row's half never leave the SM.  Online max / sum-exp / sum-exp-times-logit
+        // over the bf16-rounded logits (rp: the reference's logits tensor is bf16), plus the target's logit if it is in this half.
+        const long long tgt = row < g.M && g.targets ? g.targets[row] - (long long)n_blk * BN : -1;
+        float m_run = -INFINITY, s_run = 0.f, w_run = 0.f, t_logit = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r1[32];
+          tmem_ld_32x32(t0 + c, r1);
+          tmem_ld_wait();
+          float v[32], cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = rbf(__uint_as_float(r1[j])); cmax = fmaxf(cmax, v[j]); }
+          if (cmax > m_run) { const float sc = __expf(m_run - cmax); s_run *= sc; w_run *= sc; m_run = cmax; }
+          const int tj = (int)(tgt - c);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = __expf(v[j] - m_run);
+            s_run += e; w_run = fmaf(e, v[j], w_run);
+            if (j == tj) t_logit = v[j];
+          }
+        }
+        if (row < g.M) g.part[row * g.n_blocks + n_blk] = make_float4(m_run, s_run, w_run, t_logit);
+      } else if constexpr (EPI == EVO_EPI_GELU_GATE && BN == BN_BIG) {
 #pragma unroll 1
         for (int c = 0; c < BN / 2; c += 32) {
           uint32_t r1[32], r2[32];
@@ -265,7 +292,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int CG, int EPI, int BN>
-int launch(const evo_gemm_params* p, cudaStream_t st) {
+int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets = nullptr, float4* part = nullptr) {
   using C_ = Cfg<CG, BN>;
   CUtensorMap tmA, tmB;
   int rc;
@@ -282,6 +309,7 @@ int launch(const evo_gemm_params* p, cudaStream_t st) {
   GemmArgs g;
   g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K;
+  g.targets = targets; g.part = part;
   g.a_rows = a_rows;
   g.b_tiled = b_tiled;
   // small tile: two 64-column k-blocks per barrier round when K allows (halves the issue thread's serial rounds)
@@ -360,4 +388,50 @@ extern "C" int evo_gemm(const evo_gemm_params* p, void* stream) {
   if (p->variant == 2 || p->variant == 3) return dispatch_epi<1, BN_SMALL>(p, (cudaStream_t)stream);
   if (p->variant == 1) return dispatch_epi<1, BN_BIG>(p, (cudaStream_t)stream);
   return dispatch_epi<2, BN_BIG>(p, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused scoring head: unembed GEMM + log-softmax + gather (+ entropy); the (M, V) logits never reach HBM.
+// The GEMM's epilogue leaves one float4 of statistics per (row, 256-column half); the finish kernel folds the halves:
+//   lse = M + log(sum_j s_j e^(m_j - M)),  logprob = x_target - lse,  entropy = lse - (sum_j w_j e^(m_j - M)) / S.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void score_finish_kernel(const float4* __restrict__ part, int n_blocks, long long M, const long long* __restrict__ targets, int V,
+                                    float* __restrict__ logprobs, float* __restrict__ entropy) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float mx = -INFINITY;
+  for (int j = 0; j < n_blocks; ++j) mx = fmaxf(mx, part[row * n_blocks + j].x);
+  float S = 0.f, W = 0.f;
+  for (int j = 0; j < n_blocks; ++j) {
+    const float4 q = part[row * n_blocks + j];
+    const float sc = expf(q.x - mx);
+    S = fmaf(q.y, sc, S); W = fmaf(q.z, sc, W);
+  }
+  const float lse = mx + logf(S);
+  if (logprobs) {
+    const long long t = targets ? targets[row] : -1;
+    logprobs[row] = (t < 0 || t >= V) ? 0.f : part[row * n_blocks + (int)(t / BN_BIG)].w - lse;
+  }
+  if (entropy) entropy[row] = lse - W / S;
+}
+}  // namespace
+
+extern "C" size_t evo_unembed_score_workspace(int64_t M, int V) { return (size_t)M * (size_t)(V / BN_BIG) * sizeof(float4); }
+
+extern "C" int evo_unembed_score(const evo_score_params* p, void* stream) {
+  EVO_REQUIRE(p->M >= 0 && p->V > 0 && p->V % BN_BIG == 0, "evo_unembed_score: vocabulary (%d) must be a multiple of %d", p->V, BN_BIG);
+  EVO_REQUIRE(p->K > 0 && p->K % BK == 0, "evo_unembed_score: K (%lld) must be a multiple of %d", (long long)p->K, BK);
+  EVO_REQUIRE(((uintptr_t)p->x % 16) == 0 && ((uintptr_t)p->W % 16) == 0, "evo_unembed_score: pointers must be 16-byte aligned");
+  EVO_REQUIRE(p->logprobs == nullptr || p->targets != nullptr, "evo_unembed_score: logprobs need targets");
+  if (p->M == 0) return 0;
+  const size_t need = evo_unembed_score_workspace(p->M, p->V);
+  EVO_REQUIRE(p->workspace != nullptr && p->workspace_bytes >= need, "evo_unembed_score: workspace too small (%zu < %zu)", p->workspace_bytes, need);
+  evo_gemm_params gp = {};
+  gp.A = p->x; gp.lda = p->K; gp.W = p->W; gp.C = nullptr; gp.ldc = p->V; gp.M = p->M; gp.N = p->V; gp.K = p->K; gp.epilogue = EPI_LSE; gp.variant = 0;
+  int rc = launch<2, EPI_LSE, BN_BIG>(&gp, (cudaStream_t)stream, (const long long*)p->targets, (float4*)p->workspace);
+  if (rc) return rc;
+  score_finish_kernel<<<(unsigned)((p->M + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)p->workspace, p->V / BN_BIG, p->M, (const long long*)p->targets, p->V,
+                                                                                       p->logprobs, p->entropy);
+  return check_launch("evo_unembed_score");
 }

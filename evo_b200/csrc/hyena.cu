@@ -26,6 +26,8 @@
 #include "../../include/evo_b200.h"
 #include <algorithm>
 #include "hyena_tma.cuh"
+#include "hyena_ms.cuh"
+#include <stdlib.h>
 
 using namespace evo;
 
@@ -341,22 +343,31 @@ extern "C" int evo_hyena_fwd(const evo_hyena_params* p, void* workspace, size_t 
     static unsigned long long done_s = 0, done_o = 0;
     if ((rc = ensure_dyn_smem(hyena_scan_tma_kernel<true>, smem_bytes(STAGES), done_s))) return rc;
     if ((rc = ensure_dyn_smem(hyena_scan_tma_kernel<false>, smem_bytes(STAGES), done_o))) return rc;
-    dim3 grid(p->D / CH_PER_CTA, p->B, nseg), block(evo_hy2::THREADS);
+    // 1 (default) = mode-split kernel (hyena_ms.cuh: 8 compute warps, 4 modal states per thread); 0 = round-1 kernel
+    // (4 compute warps, 8 states per thread), kept for A/B timing and as a second implementation in the parity tests
+    const char* env_v = getenv("EVO_B200_HYENA_VARIANT");      // read per call: experiments flip it inside one process
+    const int variant = env_v ? atoi(env_v) : 1;
+    static unsigned long long done_ms = 0, done_mo = 0;
+    if ((rc = ensure_dyn_smem(evo_hy3::hyena_scan_ms_kernel<true>, smem_bytes(STAGES), done_ms))) return rc;
+    if ((rc = ensure_dyn_smem(evo_hy3::hyena_scan_ms_kernel<false>, smem_bytes(STAGES), done_mo))) return rc;
+    dim3 grid(p->D / CH_PER_CTA, p->B, nseg), block(variant == 1 ? evo_hy3::THREADS : evo_hy2::THREADS);
+    auto k_state = variant == 1 ? evo_hy3::hyena_scan_ms_kernel<true> : hyena_scan_tma_kernel<true>;
+    auto k_out = variant == 1 ? evo_hy3::hyena_scan_ms_kernel<false> : hyena_scan_tma_kernel<false>;
     // ring depth 4 (96 KB): two CTAs can co-reside and hide each other's latency when the grid exceeds the SM count.
     // An 8-deep ring for single-CTA-per-SM grids was measured and did not help (1.21 vs 1.06-1.13 ms at B=8, L=8193).
     a.nst = 4;
     const int SMEM_BYTES = smem_bytes(a.nst);
     if (p->state_only) {
-      hyena_scan_tma_kernel<true><<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
-      if ((rc = check_launch("hyena_scan_tma<state>"))) return rc;
+      k_state<<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
+      if ((rc = check_launch("hyena_scan<state>"))) return rc;
     } else {
       if (nseg > 1 && !p->reuse_segment_states) {
         dim3 g2(grid.x, grid.y, nseg - 1);
-        hyena_scan_tma_kernel<true><<<g2, block, SMEM_BYTES, st>>>(tmZ, a);
-        if ((rc = check_launch("hyena_scan_tma<state>"))) return rc;
+        k_state<<<g2, block, SMEM_BYTES, st>>>(tmZ, a);
+        if ((rc = check_launch("hyena_scan<state>"))) return rc;
       }
-      hyena_scan_tma_kernel<false><<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
-      if ((rc = check_launch("hyena_scan_tma<out>"))) return rc;
+      k_out<<<grid, block, SMEM_BYTES, st>>>(tmZ, a);
+      if ((rc = check_launch("hyena_scan<out>"))) return rc;
     }
   } else {
     Args a;

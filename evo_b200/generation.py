@@ -13,6 +13,7 @@ any length can be prefilled in one pass (`force_prompt_threshold >= len(prompt)`
 (B, D, 8, 2L) FFT temporary that forces the 128-token cap."""
 from __future__ import annotations
 
+import os
 import sys
 from typing import List, Optional, Tuple
 
@@ -33,6 +34,8 @@ class Generator:
         self.model, self.tokenizer = model, tokenizer
         self.top_k, self.top_p, self.temperature = top_k, top_p, temperature
         self.untils = ["\n\n"]
+        # the token loop runs on the GPU (model.decode_loop) whenever generation is cached; "0" keeps the per-token host loop
+        self.device_loop = os.environ.get("EVO_B200_DEVICE_LOOP", "1") != "0"
 
     # -- pieces of generate() -------------------------------------------------------------
     def _state_for(self, batch: int, device, cached: bool, given: Optional[dict]):
@@ -65,6 +68,63 @@ class Generator:
     def _pick(self, last_logits: torch.Tensor) -> torch.Tensor:
         return sample(last_logits, top_k=self.top_k, top_p=self.top_p, temperature=self.temperature)
 
+    def _generate_on_device(self, window, full_prompt, x, tail, num_tokens, state, resumed, stop_at_eos, print_generation, verbose, input_string):
+        """Same token sequence as the per-token loop below, with the loop itself on the GPU: the prompt goes
+        through one parallel forward, then ONE captured CUDA graph per token runs all blocks, picks the token
+        (evo_sample_step: forced prompt tail first, then top-k/top-p/temperature or argmax), records it and its logits and
+        feeds it back -- no host synchronisation until the end.  Differences from the reference, all report-only: the
+        per-token print and the EOS notice (Q2) come out after the loop instead of during it."""
+        tk = self.tokenizer
+        n_seq, n_tail = window.shape[0], tail.shape[1]
+        dev = window.device
+        total = n_tail + num_tokens
+        picked = torch.empty(n_seq, num_tokens, dtype=torch.long, device=dev)
+        kept_logits = torch.empty(n_seq, num_tokens, tk.vocab_size, dtype=torch.float, device=dev)
+        pick_args = dict(top_k=self.top_k, top_p=self.top_p, temperature=self.temperature)
+        first = 0
+        if resumed:
+            token = x[:, -1]
+            attn = state["mha"]
+            start = full_prompt.shape[-1] if attn.seqlen_offset == 0 else attn.seqlen_offset + 1
+            forced, n_loop = tail, total
+        else:
+            with torch.inference_mode():
+                logits, state = self.model(x, inference_params_dict=state)
+            head = logits[:, -1].contiguous()
+            if n_tail:
+                token = tail[:, 0]
+            else:
+                token = self._pick_device(head)
+                kept_logits[:, 0], picked[:, 0] = head, token
+                first = 1
+            start = full_prompt.shape[-1]                      # the reference's jump to the full prompt length (Q1)
+            forced, n_loop = tail[:, 1:], total - 1
+        if n_loop > 0:
+            got, got_logits = self.model.decode_loop(token, state, n_loop, start, forced=forced if forced.shape[1] else None,
+                                                     n_out=num_tokens - first, **pick_args)
+            picked[:, first:], kept_logits[:, first:] = got, got_logits
+        if stop_at_eos and num_tokens >= 2 and bool((picked[0, -2:] == tk.eos).all()):
+            print("Stopping generation at EOS")              # report only, as in the reference (Q2)
+        if print_generation and verbose and n_seq == 1:
+            for t in torch.cat([tail[0], picked[0]]).tolist():
+                print(tk.detokenize([t]), end=" ")
+        if verbose:
+            shown = tk.detokenize_batch(picked)
+            shown = [t.split(stop)[0] if stop in t else t for t in shown for stop in self.untils[:1]]
+            print(f"\n[generate] in: {input_string} | out: {shown} | {_gb(dev):.2f} GB allocated")
+        return picked, kept_logits, state
+
+    def _pick_device(self, head: torch.Tensor) -> torch.Tensor:
+        """One call of the device sampler (evo_sample) on (B, V) bf16 logits."""
+        import ctypes as C
+        from . import _lib
+        out = torch.empty(head.shape[0], dtype=torch.long, device=head.device)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        head = head.to(torch.bfloat16).contiguous()
+        _lib.check(_lib.lib().evo_sample(_lib.ptr(head), _lib.ptr(out), head.shape[0], head.shape[1], int(self.top_k), float(self.top_p), float(self.temperature),
+                                         seed, 0, C.c_void_p(torch.cuda.current_stream(head.device).cuda_stream)), "evo_sample")
+        return out
+
     # -- public ---------------------------------------------------------------------------
     def generate(self, device: str, input_string: str = None, input_ids: torch.Tensor = None, num_tokens: int = 32,
                  cached_generation: bool = True, force_prompt_threshold: int = 128, print_generation: bool = True,
@@ -90,6 +150,9 @@ class Generator:
         if verbose:
             what = f"prompt {input_string!r}" if input_string is not None else f"prompt ids {tuple(input_ids.shape)}"
             print(f"[generate] {what}; {_gb(dev):.2f} GB allocated; prefill {x.shape[1]} + forced {n_tail} + new {num_tokens}")
+
+        if cached_generation and self.device_loop and hasattr(self.model, "decode_loop") and window.is_cuda and n_tail + num_tokens > 0:
+            return self._generate_on_device(window, full_prompt, x, tail, num_tokens, state, resumed, stop_at_eos, print_generation, verbose, input_string)
 
         last_step = -1
         for last_step in range(n_tail + num_tokens):

@@ -76,13 +76,16 @@ def _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, s
     dev = qkv.device
     L = Lr * world
     # (B, Lr, 3, P, Hl, hd) -> (P, B, Lr, 3, Hl, hd): chunk p goes to rank p
-    send = qkv.view(B, Lr, 3, world, Hl, hd).permute(3, 0, 1, 2, 4, 5).contiguous()
+    box = {}
+    model._record("comm/permute", 2.0 * qkv.numel() * 2, lambda: box.__setitem__("send", qkv.view(B, Lr, 3, world, Hl, hd).permute(3, 0, 1, 2, 4, 5).contiguous()))
+    send = box["send"]
     recv = torch.empty_like(send)                     # (P = source rank = sequence chunk, B, Lr, 3, Hl, hd)
-    dist.all_to_all_single(recv, send, group=group)
+    model._record("comm/all_to_all", send.numel() * 2.0 * (world - 1) / world, lambda: dist.all_to_all_single(recv, send, group=group))
     if B == 1:
         full = recv.view(1, L, 3, Hl, hd)             # source-rank order is sequence order
     else:
-        full = recv.permute(1, 0, 2, 3, 4, 5).reshape(B, L, 3, Hl, hd).contiguous()
+        model._record("comm/permute", 2.0 * recv.numel() * 2, lambda: box.__setitem__("full", recv.permute(1, 0, 2, 3, 4, 5).reshape(B, L, 3, Hl, hd).contiguous()))
+        full = box["full"]
     dl = Hl * hd
     out = torch.empty(B, L, dl, dtype=torch.bfloat16, device=dev)
     ap = AttnParams(out=out.data_ptr(), B=B, Lq=L, Lk=L, H=Hl, hd=hd, q_pos0=0, softmax_scale=1.0 / math.sqrt(hd))
@@ -93,10 +96,14 @@ def _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, s
     causal_flops = 4.0 * B * Hl * hd * (L * (L + 1) / 2.0)
     model._record("attn", causal_flops, lambda: check(lib.evo_attn_fwd_ws(C.byref(ap), model.attn_variant, ptr(ws), n, stream()), "evo_attn_fwd"))
     # back: (B, P, Lr, Hl*hd) -> chunk p (its tokens, my heads) to rank p
-    send2 = out.view(B, world, Lr, dl).permute(1, 0, 2, 3).contiguous()
+    if B == 1:
+        send2 = out.view(world, B, Lr, dl)            # chunk p = tokens of rank p: already contiguous
+    else:
+        model._record("comm/permute", 2.0 * out.numel() * 2, lambda: box.__setitem__("send2", out.view(B, world, Lr, dl).permute(1, 0, 2, 3).contiguous()))
+        send2 = box["send2"]
     recv2 = torch.empty_like(send2)                   # (P = head group, B, Lr, dl)
-    dist.all_to_all_single(recv2, send2, group=group)
-    ctx.view(B, Lr, world, dl).copy_(recv2.permute(1, 2, 0, 3))
+    model._record("comm/all_to_all", send2.numel() * 2.0 * (world - 1) / world, lambda: dist.all_to_all_single(recv2, send2, group=group))
+    model._record("comm/permute", 2.0 * recv2.numel() * 2, lambda: ctx.view(B, Lr, world, dl).copy_(recv2.permute(1, 2, 0, 3)))
 
 
 def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: int, group=None, transport: str = "auto"):
@@ -135,7 +142,7 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
         if pc is False:
             pc = None
         if pc is not None:
-            dist.barrier(group)          # nobody is still reading ring slots of the previous forward
+            model._record("comm/barrier", 0.0, lambda: dist.barrier(group))          # nobody is still reading ring slots of the previous forward
     since_sync = 0
     with torch.cuda.device(dev), torch.no_grad():
         ids_local = ids_local.contiguous()
@@ -164,20 +171,24 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 tail = z.view(B, Lr, 3 * d)[:, -2:].contiguous()
                 if pc is not None:
                     if since_sync == pc.NBUF:
-                        dist.barrier(group)
+                        model._record("comm/barrier", 0.0, lambda: dist.barrier(group))
                         since_sync = 0
                     k = since_sync
                     since_sync += 1
                     pc.epoch += 1
                     if rank + 1 < world:
-                        check(lib.evo_peer_publish(ptr(tail), pc.halo_bytes, ptr(pc.halo_dsts[k]), ptr(pc.hflag_dsts[k]), 0, rank, rank + 1, rank + 1,
-                                                   pc.epoch, ptr(pc.counter), stream()), "evo_peer_publish(halo)")
+                        model._record("comm/peer_halo", float(pc.halo_bytes), lambda: check(lib.evo_peer_publish(
+                            ptr(tail), pc.halo_bytes, ptr(pc.halo_dsts[k]), ptr(pc.hflag_dsts[k]), 0, rank, rank + 1, rank + 1,
+                            pc.epoch, ptr(pc.counter), stream()), "evo_peer_publish(halo)"))
                     halo = None
                     if rank > 0:
-                        check(lib.evo_peer_wait(ptr(pc.local(k, pc.off_hflag, world * 4)), rank - 1, rank - 1, pc.epoch, stream()), "evo_peer_wait(halo)")
+                        model._record("comm/peer_halo", 0.0, lambda: check(lib.evo_peer_wait(
+                            ptr(pc.local(k, pc.off_hflag, world * 4)), rank - 1, rank - 1, pc.epoch, stream()), "evo_peer_wait(halo)"))
                         halo = pc.local(k, pc.off_halo, pc.halo_bytes)
                 else:
-                    tails = _all_gather(tail, world, group)                                   # (W, B, 2, 3D)
+                    box = {}
+                    model._record("comm/all_gather", float(tail.numel() * 2 * (world - 1)), lambda: box.__setitem__("t", _all_gather(tail, world, group)))   # (W, B, 2, 3D)
+                    tails = box["t"]
                     halo = tails[rank - 1].contiguous() if rank > 0 else None
                 end = torch.empty(B, d, S, 2, dtype=torch.float32, device=dev)
                 hp = HyenaParams(z=z.data_ptr(), y=None, fir_w=f.short_filter_weight.data_ptr(), fir_b=f.short_filter_bias.data_ptr(), Dskip=f.D.data_ptr(),
@@ -189,15 +200,19 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 model._record("hyena_state", 4.0 * B * Lr * d, lambda: check(lib.evo_hyena_fwd(C.byref(hp), ptr(ws), n, stream()), "evo_hyena_fwd(state)"))
                 if pc is not None:
                     if rank + 1 < world:   # only later shards need my end state
-                        check(lib.evo_peer_publish(ptr(end), pc.end_bytes, ptr(pc.ends_dsts[k]), ptr(pc.eflag_dsts[k]), pc.end_bytes, rank, rank + 1, world - 1,
-                                                   pc.epoch, ptr(pc.counter), stream()), "evo_peer_publish(end)")
+                        model._record("comm/peer_state", float(pc.end_bytes * (world - 1 - rank)), lambda: check(lib.evo_peer_publish(
+                            ptr(end), pc.end_bytes, ptr(pc.ends_dsts[k]), ptr(pc.eflag_dsts[k]), pc.end_bytes, rank, rank + 1, world - 1,
+                            pc.epoch, ptr(pc.counter), stream()), "evo_peer_publish(end)"))
                     if rank > 0:
-                        check(lib.evo_peer_wait(ptr(pc.local(k, pc.off_eflag, world * 4)), 0, rank - 1, pc.epoch, stream()), "evo_peer_wait(end)")
+                        model._record("comm/peer_state", 0.0, lambda: check(lib.evo_peer_wait(
+                            ptr(pc.local(k, pc.off_eflag, world * 4)), 0, rank - 1, pc.epoch, stream()), "evo_peer_wait(end)"))
                     ends = pc.local(k, 0, world * pc.end_bytes)
                 else:
-                    ends = _all_gather(end, world, group)                                  # (W, B, D, S, 2)
+                    box = {}
+                    model._record("comm/all_gather", float(end.numel() * 4 * (world - 1)), lambda: box.__setitem__("e", _all_gather(end, world, group)))   # (W, B, D, S, 2)
+                    ends = box["e"]
                 s_in = torch.empty_like(end)
-                check(lib.evo_hyena_combine_states(ptr(ends), ptr(s_in), ptr(f.poles), rank, world, Lr, B, d, S, stream()), "evo_hyena_combine_states")
+                model._record("hyena_combine", 0.0, lambda: check(lib.evo_hyena_combine_states(ptr(ends), ptr(s_in), ptr(f.poles), rank, world, Lr, B, d, S, stream()), "evo_hyena_combine_states"))
                 y = xn
                 # output pass: same geometry, so the per-segment end states of the carry pass are reused from `ws`
                 hp.y, hp.state_in, hp.state_out, hp.state_only, hp.reuse_segment_states = y.data_ptr(), s_in.data_ptr(), None, 0, 1

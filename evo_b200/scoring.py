@@ -63,12 +63,16 @@ def score_sequences(seqs: List[str], model, tokenizer: CharLevelTokenizer, reduc
     if reduce_method not in ("mean", "sum"):
         raise ValueError(f"Invalid reduce_method {reduce_method}")
     input_ids, lengths = prepare_batch(seqs, tokenizer, device=device, prepend_bos=True)
-    with torch.inference_mode():
-        logits, _ = model(input_ids)
-    if logits.is_cuda and logits.dtype == torch.bfloat16 and logits.is_contiguous():
-        logprobs = _fused_logprobs(logits, input_ids)
+    if hasattr(model, "score_tokens") and input_ids.is_cuda:
+        # fused head: unembed + log-softmax + gather in the GEMM epilogue, logits never written
+        logprobs = model.score_tokens(input_ids, want_logprobs=True)[0][:, :-1]
     else:
-        logprobs = logits_to_logprobs(logits, input_ids, trim_bos=True).float()
+        with torch.inference_mode():
+            logits, _ = model(input_ids)
+        if logits.is_cuda and logits.dtype == torch.bfloat16 and logits.is_contiguous():
+            logprobs = _fused_logprobs(logits, input_ids)
+        else:
+            logprobs = logits_to_logprobs(logits, input_ids, trim_bos=True).float()
     logprobs = logprobs.cpu().numpy()
     reduce = np.mean if reduce_method == "mean" else np.sum
     return [reduce(logprobs[i][:n]) for i, n in enumerate(lengths)]
@@ -76,10 +80,13 @@ def score_sequences(seqs: List[str], model, tokenizer: CharLevelTokenizer, reduc
 
 def positional_entropies(seqs: List[str], model, tokenizer: CharLevelTokenizer, device: str = "cuda:0") -> List[np.ndarray]:
     input_ids, lengths = prepare_batch(seqs, tokenizer, device=device, prepend_bos=True)
-    with torch.inference_mode():
-        logits, _ = model(input_ids)
-    lp = torch.log_softmax(logits.float(), dim=-1)[:, :-1]
-    ent = -(lp.exp() * lp).sum(dim=-1).cpu().numpy()
+    if hasattr(model, "score_tokens") and input_ids.is_cuda:
+        ent = model.score_tokens(input_ids, want_logprobs=False, want_entropy=True)[1][:, :-1].cpu().numpy()
+    else:
+        with torch.inference_mode():
+            logits, _ = model(input_ids)
+        lp = torch.log_softmax(logits.float(), dim=-1)[:, :-1]
+        ent = -(lp.exp() * lp).sum(dim=-1).cpu().numpy()
     out = [ent[i][:n] for i, n in enumerate(lengths)]
     if any(len(s) != len(e) for s, e in zip(seqs, out)):
         raise AssertionError("entropy length mismatch")

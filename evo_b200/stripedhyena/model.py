@@ -162,6 +162,7 @@ class StripedHyena(nn.Module):
         self._smallm_ws = None
         self._tiled = None   # tile-major weight copies for the weight-streaming decode GEMMs
         self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
+        self._loop = None    # cached CUDA graph of one step of the on-device generation loop (see decode_loop)
         self._prof = None   # set to a list to record (kind, algorithmic work, start event, end event) per kernel call
 
     # ---- reference API ------------------------------------------------------------------
@@ -184,6 +185,7 @@ class StripedHyena(nn.Module):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._packed = None
         self._decode = None
+        self._loop = None
         self._tiled = None
         return out
 
@@ -192,6 +194,7 @@ class StripedHyena(nn.Module):
         self._packed = None
         self._rope = None
         self._decode = None
+        self._loop = None
         self._tiled = None
         return out
 
@@ -410,23 +413,59 @@ class StripedHyena(nn.Module):
             with torch.cuda.device(dev), torch.no_grad():
                 return self._decode_forward(x, inference_params_dict), inference_params_dict
         with torch.cuda.device(dev), torch.no_grad():
-            u = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
-            check(_lib.lib().evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u),
-                                       M, d, V, self._stream()), "evo_embed")
-            for i, blk in enumerate(self.blocks):
-                if i in self._attn_idxs:
-                    ip = inference_params_dict["mha"] if inference_params_dict is not None else None
-                    u = self._attention_block(i, blk, u, B, L, ip)
-                else:
-                    ip = inference_params_dict["hyena"] if inference_params_dict is not None else None
-                    u = self._hyena_block(i, blk, u, B, L, ip)
-            if self.norm is not None:
-                xn = torch.empty_like(u)
-                self._rmsnorm(u, self.norm.scale, xn, M)
-                u = xn
+            u = self._backbone(x, B, L, inference_params_dict)
             logits = torch.empty(M, V, dtype=torch.bfloat16, device=dev)
             self._gemm(u, self.unembed.weight, logits, M, V, d, EPI_NONE)
         return logits.view(B, L, V), inference_params_dict
+
+    def _backbone(self, x, B, L, inference_params_dict=None):
+        """embed -> all blocks -> final norm: the (B*L, D) bf16 input of the unembedding."""
+        M, d, V = B * L, self.config.hidden_size, self.config.vocab_size
+        dev = x.device
+        u = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
+        check(_lib.lib().evo_embed(ptr(x), int(x.dtype == torch.int64), ptr(self.embedding_layer.weight), ptr(u),
+                                   M, d, V, self._stream()), "evo_embed")
+        for i, blk in enumerate(self.blocks):
+            if i in self._attn_idxs:
+                ip = inference_params_dict["mha"] if inference_params_dict is not None else None
+                u = self._attention_block(i, blk, u, B, L, ip)
+            else:
+                ip = inference_params_dict["hyena"] if inference_params_dict is not None else None
+                u = self._hyena_block(i, blk, u, B, L, ip)
+        if self.norm is not None:
+            xn = torch.empty_like(u)
+            self._rmsnorm(u, self.norm.scale, xn, M)
+            u = xn
+        return u
+
+    def score_tokens(self, input_ids, want_logprobs=True, want_entropy=False):
+        """Fused scoring head: what evo/scoring.py computes from `model(input_ids)` -- log_softmax of the
+        logits gathered at the NEXT token (logits_to_logprobs, :36-59) and the per-position entropy (:119-121) -- without
+        the (B, L, 512) logits ever reaching HBM: the unembed GEMM's epilogue keeps max / sum-exp / sum-exp*logit / target
+        logit per row (evo_unembed_score).  Returns (logprobs (B, L) fp32 or None, entropy (B, L) fp32 or None);
+        logprobs[b, t] = log p(ids[b, t+1] | ids[b, :t+1]), 0 at the last position."""
+        if input_ids.dim() != 2 or input_ids.dtype not in (torch.int32, torch.int64):
+            raise TypeError("input ids must be (batch, length) int32/int64")
+        self._ensure_packed()
+        dev = self.embedding_layer.weight.device
+        if input_ids.device != dev:
+            raise _lib.EvoError(f"input ids on {input_ids.device}, model on {dev}")
+        x = input_ids.contiguous()
+        B, L = x.shape
+        M, d, V = B * L, self.config.hidden_size, self.config.vocab_size
+        lib = _lib.lib()
+        with torch.cuda.device(dev), torch.no_grad():
+            u = self._backbone(x, B, L, None)
+            targets = torch.full((B, L), -1, dtype=torch.long, device=dev)
+            targets[:, :-1] = x[:, 1:]
+            lp = torch.empty(B, L, dtype=torch.float32, device=dev) if want_logprobs else None
+            ent = torch.empty(B, L, dtype=torch.float32, device=dev) if want_entropy else None
+            n = lib.evo_unembed_score_workspace(M, V)
+            ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+            sp = _lib.ScoreParams(x=u.data_ptr(), W=self.unembed.weight.data_ptr(), targets=targets.data_ptr(), logprobs=lp.data_ptr() if lp is not None else None,
+                                  entropy=ent.data_ptr() if ent is not None else None, M=M, V=V, K=d, workspace=ws.data_ptr(), workspace_bytes=n)
+            self._record(f"gemm/{V}x{d}/score", 2.0 * M * V * d, lambda: check(lib.evo_unembed_score(C.byref(sp), self._stream()), "evo_unembed_score"))
+        return lp, ent
 
     # ---- decode step: small-M weight-streaming GEMM tiles + device-side position + CUDA graph ------
     def _can_step(self, ipd, B):
@@ -540,6 +579,96 @@ class StripedHyena(nn.Module):
         logits = torch.empty(B, V, dtype=torch.bfloat16, device=dev)
         lin(u, tiled["unembed"] if tiled is not None else self.unembed.weight, logits, V, d, EPI_NONE)
         return logits
+
+    # ---- on-device generation loop: token pick + bookkeeping + feedback inside the captured step ------
+    def decode_loop(self, first_token, ipd, n_steps, start_pos, *, top_k=1, top_p=0.0, temperature=1.0, forced=None, n_out=None, seed=None):
+        """Run `n_steps` single-token steps without returning to the host in between.
+
+        first_token (B,) or (B, 1): the input of step 0; ipd: populated state (after a prefill); start_pos: sequence
+        position of step 0 (the reference sets the FULL prompt length here, evo/generation.py:143).  Step i feeds the
+        token of step i-1; the token of step i is forced[:, i] while i < forced.shape[1] (teacher-forced prompt tail,
+        evo/generation.py:156-160), afterwards it is picked on the device by evo_sample_step.
+        Returns (picked (B, n_out) int64, kept_logits (B, n_out, V) fp32) for the sampled steps; the state holders'
+        seqlen_offset end at the value the per-token protocol would leave.
+        One CUDA graph = one whole step (all blocks + sampler + counters); the host only replays it."""
+        lib = _lib.lib()
+        dev = self.embedding_layer.weight.device
+        x = first_token.reshape(-1, 1).contiguous()
+        B = x.shape[0]
+        V = self.config.vocab_size
+        if not self._can_step(ipd, B):
+            raise _lib.EvoError("decode_loop needs populated inference params (run the prefill first)")
+        mha_ip, hy_ip = ipd["mha"], ipd["hyena"]
+        n_forced = 0 if forced is None else int(forced.shape[1])
+        n_out = n_steps - n_forced if n_out is None else n_out
+        if n_out < 0:
+            raise ValueError("more forced tokens than steps")
+        for i in mha_ip.key_value_memory_dict:
+            if start_pos + n_steps > mha_ip.key_value_memory_dict[i].shape[1]:
+                raise _lib.EvoError(f"sequence length {start_pos + n_steps} exceeds the KV cache ({mha_ip.key_value_memory_dict[i].shape[1]}) (mha.py:367)")
+        with torch.cuda.device(dev), torch.no_grad():
+            self._ensure_packed()
+            for i in list(hy_ip.state_dict):
+                hy_ip.state_dict[i] = hy_ip.state_dict[i].contiguous()
+                hy_ip.fir_state_dict[i] = hy_ip.fir_state_dict[i].contiguous()
+            picked = torch.empty(B, max(n_out, 1), dtype=torch.long, device=dev)
+            kept = torch.empty(B, max(n_out, 1), V, dtype=torch.float32, device=dev)
+            forced_c = forced.to(dev, torch.long).contiguous() if n_forced else None
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # torch.manual_seed() governs reproducibility
+            lp = _lib.LoopParams(forced=forced_c.data_ptr() if n_forced else None, n_forced=n_forced, forced_stride=n_forced,
+                                 picked=picked.data_ptr(), picked_stride=picked.shape[1], kept_logits=kept.data_ptr(), n_out=n_out,
+                                 top_k=int(top_k), top_p=float(top_p), temperature=float(temperature), seed=seed, step0=0)
+            key = ("loop", B, tuple(hy_ip.state_dict[i].data_ptr() for i in sorted(hy_ip.state_dict)),
+                   tuple(hy_ip.fir_state_dict[i].data_ptr() for i in sorted(hy_ip.fir_state_dict)),
+                   tuple((mha_ip.key_value_memory_dict[i].data_ptr(), mha_ip.key_value_memory_dict[i].shape[1]) for i in sorted(mha_ip.key_value_memory_dict)))
+            st = self._loop
+            if st is None or st["key"] != key:
+                st = {"key": key, "graph": None, "x": torch.empty(B, 1, dtype=torch.long, device=dev), "pos": torch.zeros(1, dtype=torch.int64, device=dev),
+                      "step": torch.zeros(1, dtype=torch.int64, device=dev), "lp": torch.zeros(C.sizeof(_lib.LoopParams), dtype=torch.uint8, device=dev),
+                      "lp_host": torch.zeros(C.sizeof(_lib.LoopParams), dtype=torch.uint8).pin_memory()}
+                self._loop = st
+            C.memmove(st["lp_host"].data_ptr(), C.addressof(lp), C.sizeof(lp))
+            st["lp"].copy_(st["lp_host"], non_blocking=True)
+            st["pos"].fill_(int(start_pos))
+            st["step"].zero_()
+            st["x"].copy_(x.to(torch.long))
+
+            def one_step():
+                logits = self._decode_body(st["x"], st["pos"], ipd, B)
+                prev = lib.evo_set_pdl(int(self.decode_pdl))
+                try:
+                    check(lib.evo_sample_step(ptr(logits), ptr(st["x"]), B, V, ptr(st["lp"]), ptr(st["step"]), self._stream()), "evo_sample_step")
+                    check(lib.evo_advance_counters(ptr(st["pos"]), ptr(st["step"]), 1, self._stream()), "evo_advance_counters")
+                finally:
+                    lib.evo_set_pdl(prev)
+
+            done = 0
+            if st["graph"] is None or st.get("ptrs") != self._graph_ptrs():
+                one_step()                      # eager step: allocates rope tables / workspaces the capture must not
+                done = 1
+                if self.decode_graph and n_steps > 1:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    n0 = lib.evo_launch_count()
+                    with torch.cuda.graph(g):
+                        one_step()
+                    st["graph"], st["launches"], st["ptrs"] = g, lib.evo_launch_count() - n0, self._graph_ptrs()
+                    lib.evo_note_graph_replay(-st["launches"])
+            for _ in range(done, n_steps):
+                if st["graph"] is not None:
+                    st["graph"].replay()
+                    lib.evo_note_graph_replay(st["launches"])
+                else:
+                    one_step()
+            end = int(start_pos) + n_steps - 1          # the position the last step ran at (what the per-token protocol leaves)
+            mha_ip.seqlen_offset = hy_ip.seqlen_offset = end
+            # the captured graph and its buffers stay alive in self._loop; the outputs are this call's own tensors
+            return picked[:, :n_out], kept[:, :n_out]
+
+    def _graph_ptrs(self):
+        """Addresses a captured step bakes in besides the state tensors: rope tables and the stream-K workspace."""
+        return (tuple(t.data_ptr() for t in (self._rope or ())), self._smallm_ws.data_ptr() if self._smallm_ws is not None else 0)
 
     def _decode_forward(self, x, ipd):
         """L == 1 with populated states.  Step 1 after a prefill runs eagerly (and makes the state

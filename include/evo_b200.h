@@ -189,6 +189,31 @@ int evo_decode_attn(const void* qkv, const void* cache, void* out, const int64_t
                     int64_t max_seqlen, int nsplit, float softmax_scale, void* workspace, size_t workspace_bytes, void* stream);
 int evo_advance_position(int64_t* pos, int64_t delta, void* stream);
 
+/* ---- device-side sampler and generation loop: stripedhyena.sample.sample (evo/generation.py:162-167) and the host half
+ * of the token loop (evo/generation.py:131-189) ----
+ * evo_sample: logits (B, V) bf16 -> out (B) int64.  top_k == 1: argmax (first maximum); otherwise top-k (top_k <= 0:
+ *   whole vocabulary) -> / temperature (bf16-rounded like the reference's tensor op) -> top-p tail mask (entries whose
+ *   cumulative mass counted from the smallest up is <= 1 - top_p) -> multinomial.  Randomness: Philox4x32-10 keyed by
+ *   (seed, step, row) -- reproducible, independent of launch order, CUDA-graph friendly.  V <= 1024.
+ * evo_sample_step: the same inside the on-device loop.  Step index i = *step_dev (device); while i < n_forced the
+ *   token is forced[row, i] (teacher-forced prompt tail), afterwards it is sampled with RNG step step0 + i and recorded:
+ *   picked[row, i - n_forced] = token, kept_logits[row, i - n_forced, :] = float(logits[row]).  The token is also
+ *   written to x[row], the next step's input.  All of evo_loop_params lives in DEVICE memory, so one captured graph
+ *   serves every generate() call.
+ * evo_advance_counters: *a += delta, *b += delta (either may be NULL). */
+typedef struct {
+  const int64_t* forced; int64_t n_forced; int64_t forced_stride;   /* (B, n_forced) int64 */
+  int64_t* picked; int64_t picked_stride;                          /* (B, n_out) int64 or NULL */
+  float* kept_logits; int64_t n_out;                               /* (B, n_out, V) fp32 or NULL */
+  int32_t top_k; float top_p; float temperature;
+  uint64_t seed; int64_t step0;
+} evo_loop_params;
+int evo_sample(const void* logits, int64_t* out, int B, int V, int top_k, float top_p, float temperature,
+               uint64_t seed, uint64_t step, void* stream);
+int evo_sample_step(const void* logits, int64_t* x, int B, int V, const evo_loop_params* loop_params_dev,
+                    const int64_t* step_dev, void* stream);
+int evo_advance_counters(int64_t* a, int64_t* b, int64_t delta, void* stream);
+
 /* (test comparators -- cuBLASLt GEMM, CUDA-core attention, bf16 add -- live in tests/support/libevo_b200_test.so,
  *  not in this library) */
 
@@ -196,6 +221,23 @@ int evo_advance_position(int64_t* pos, int64_t delta, void* stream);
  * logits (rows, V) bf16; targets (rows) int64 (-1 = skip -> 0); out (rows) fp32 =
  * log_softmax(logits)[target], fp32 statistics. */
 int evo_logprobs(const void* logits, const int64_t* targets, float* out, int64_t rows, int V, void* stream);
+
+
+/* ---- fused scoring head: unembed (tied embedding, N = vocab) + log_softmax + gather + entropy in one pass; the
+ * (rows, V) logits never reach HBM (evo/scoring.py:36-59 logits_to_logprobs, :119-121 positional_entropies).
+ * x (M, K) bf16 = final-norm output; W (V, K) bf16; targets (M) int64 (-1 = none -> logprob 0) or NULL.
+ * logprobs[r] = bf16(x_r . W_t) - logsumexp_v(bf16(x_r . W_v)) in fp32 -- the logits are rounded to bf16 exactly where
+ * the reference's logits tensor is, the statistics are fp32 (the reference's own log_softmax runs in bf16, quirk Q4);
+ * entropy[r] = -sum_v p_v log p_v over the same distribution.  Either output may be NULL.  V % 256 == 0, K % 64 == 0. */
+typedef struct {
+  const void* x; const void* W;
+  const int64_t* targets;
+  float* logprobs; float* entropy;
+  int64_t M; int V; int64_t K;
+  void* workspace; size_t workspace_bytes;     /* evo_unembed_score_workspace(M, V) bytes */
+} evo_score_params;
+size_t evo_unembed_score_workspace(int64_t M, int V);
+int evo_unembed_score(const evo_score_params* p, void* stream);
 
 #ifdef __cplusplus
 }
