@@ -93,6 +93,7 @@ SIGNATURES = {
     "evo_advance_counters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "evo_unembed_score_workspace": (C.c_size_t, [C.c_int64, C.c_int]),
     "evo_unembed_score": (C.c_int, [C.POINTER(ScoreParams), C.c_void_p]),
+    "evo_tokenize_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "evo_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
 }
 

@@ -53,12 +53,14 @@ def _resolve_config(model_name: str, config_path: Optional[str]) -> dict:
 
 
 def load_checkpoint(model_name: str = "evo-1-8k-base", config_path: Optional[str] = None, device: str = None,
-                    model_dir: Optional[str] = None, random_init: bool = False, seed: int = 0, *args, **kwargs):
+                    model_dir: Optional[str] = None, random_init: bool = False, seed: int = 0, streaming: bool = True, *args, **kwargs):
     """HF snapshot -> safetensors -> StripedHyena on `device`.
 
     model_dir: use an already-downloaded snapshot directory instead of huggingface_hub.
     random_init: skip the checkpoint (benchmarks / tests on boxes without network) and keep the
-    constructor's random initialisation, seeded."""
+    constructor's random initialisation, seeded.
+    streaming: True (default) = tensor-by-tensor ingest straight into the device layouts; False = the reference's
+    host-state-dict sequence (kept as the comparator for the ingest tests)."""
     cfg = dotdict(_resolve_config(model_name, config_path))
 
     if random_init:
@@ -66,11 +68,14 @@ def load_checkpoint(model_name: str = "evo-1-8k-base", config_path: Optional[str
         torch.manual_seed(seed)
         with torch.device(device if device is not None else "cpu"):
             model = StripedHyena(cfg)
-    else:
-        if model_dir is None:
-            from huggingface_hub import snapshot_download
-            _, repo, revision = MODELS[model_name]
-            model_dir = snapshot_download(repo, revision=revision)
+        model.to_bfloat16_except_poles_residues()
+        return model if device is None else model.to(device)
+    if model_dir is None:
+        from huggingface_hub import snapshot_download
+        _, repo, revision = MODELS[model_name]
+        model_dir = snapshot_download(repo, revision=revision)
+    if not streaming:
+        # the reference's own sequence (evo/models.py:96-150): host state dict -> strict load -> bf16 -> device
         state = {}
         for key, value in _read_safetensors(model_dir).items():
             state[key[len("backbone."):] if key.startswith("backbone.") else key] = value
@@ -78,9 +83,17 @@ def load_checkpoint(model_name: str = "evo-1-8k-base", config_path: Optional[str
             state["unembed.weight"] = state["embedding_layer.weight"]
         model = StripedHyena(cfg)
         model.load_state_dict(state, strict=True)
+        model.to_bfloat16_except_poles_residues()
+        return model if device is None else model.to(device)
+    # streaming ingest: parameters are allocated once, on the target device, in their final dtype and layout;
+    # each checkpoint tensor goes mmap -> pinned staging -> device and is cast / packed there (evo_b200/ingest.py)
+    from .ingest import load_streaming
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    with torch.device("meta"):
+        model = StripedHyena(cfg)
     model.to_bfloat16_except_poles_residues()
-    if device is not None:
-        model = model.to(device)
+    model = model.to_empty(device=dev)
+    model.ingest_stats = load_streaming(model, model_dir, dev)
     return model
 
 

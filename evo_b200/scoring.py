@@ -2,10 +2,12 @@
 reference's evo/scoring.py (prepare_batch :9-33, logits_to_logprobs :36-59,
 score_sequences :62-96, positional_entropies :99-131).
 
-Differences, all inside the contract: the batch is assembled on the host and moved with
-ONE pinned host->device copy (the reference does one per sequence, :22-30), and
-score_sequences reads the per-token log-likelihood through the fused evo_logprobs kernel
-(fp32 statistics instead of the reference's bf16 log_softmax, quirk Q4 in SURVEY.md 8c)."""
+Differences, all inside the contract: the sequences' bytes move with ONE pinned host->device
+copy of 1 byte per nucleotide and the id matrix is built on the GPU (the reference does one int64
+copy per sequence, :22-30); score_sequences / positional_entropies read log-likelihood and entropy
+from the fused scoring head (model.score_tokens: unembed GEMM + log-softmax + gather in one kernel,
+the (B, L, 512) logits are never written; fp32 statistics instead of the reference's bf16
+log_softmax, quirk Q4 in SURVEY.md 8c)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -20,7 +22,11 @@ from .tokenizer import CharLevelTokenizer
 
 def prepare_batch(seqs: List[str], tokenizer: CharLevelTokenizer, prepend_bos: bool = True,
                   device: str = "cuda:0") -> Tuple[torch.Tensor, List[int]]:
-    """(B, bos + max_len) int64 ids, right-padded with pad_id, BOS = eod_id."""
+    """(B, bos + max_len) int64 ids, right-padded with pad_id, BOS = eod_id.
+    On a CUDA device the bytes go over once as uint8 and the id matrix is written there (frontend.device_batch)."""
+    if torch.device(device).type == "cuda" and torch.cuda.is_available():
+        from .frontend import device_batch
+        return device_batch(seqs, tokenizer, prepend_bos=prepend_bos, device=device)
     lengths = [len(s) for s in seqs]
     width = max(lengths) + int(prepend_bos)
     host = torch.full((len(seqs), width), tokenizer.pad_id, dtype=torch.long)

@@ -57,7 +57,29 @@ class _Linear(nn.Module):
         self.bias = nn.Parameter(torch.zeros(fan_out)) if bias else None
 
 
+def pack_w12(l1: torch.Tensor, l2: torch.Tensor, ipad: int) -> torch.Tensor:
+    """(inner, K) x 2 -> (2*ipad, K): rows interleaved in 128-row groups [l1 rows g*128.. | l2 rows g*128..], zero rows past
+    `inner`, so one 128x256 accumulator tile holds l1.x and l2.x of the same 128 inner features (gate fused in the epilogue)."""
+    inner, k = l1.shape
+    out = l1.new_zeros(ipad // 128, 2, 128, k)
+    out[:, 0] = F.pad(l1, (0, 0, 0, ipad - inner)).view(ipad // 128, 128, k)
+    out[:, 1] = F.pad(l2, (0, 0, 0, ipad - inner)).view(ipad // 128, 128, k)
+    return out.view(2 * ipad, k)
+
+
+def unpack_w12(w12: torch.Tensor, inner: int):
+    ipad, k = w12.shape[0] // 2, w12.shape[1]
+    v = w12.view(ipad // 128, 2, 128, k)
+    return v[:, 0].reshape(ipad, k)[:inner], v[:, 1].reshape(ipad, k)[:inner]
+
+
 class _GatedMLP(nn.Module):
+    """ParallelGatedMLP parameters, held ONLY in the layouts the GEMMs read (no second copy):
+      w12 (2*ipad, D)  l1 / l2 interleaved per 128 rows, zero-padded 10928 -> 11008 (pack_w12)
+      w3  (D, ipad)    l3 zero-padded along K
+    The checkpoint's key names (mlp.l1.weight, mlp.l2.weight, mlp.l3.weight; evo/models.py:124-147) are what state_dict()
+    shows and what load_state_dict() accepts: two hooks translate at the module boundary."""
+
     def __init__(self, cfg):
         super().__init__()
         d = cfg.hidden_size
@@ -67,10 +89,37 @@ class _GatedMLP(nn.Module):
             inner = cfg.get("inner_mlp_size")
         if (cfg.get("mlp_activation") or "silu") != "gelu":
             raise NotImplementedError("evo_b200 implements the Evo configs' exact-erf GELU gate only")
-        self.inner = inner
-        self.l1 = _Linear(d, inner, False)
-        self.l2 = _Linear(d, inner, False)
-        self.l3 = _Linear(inner, d, False)
+        self.inner, self.ipad = inner, _round_up(inner, 128)
+        mk = lambda fo, fi: torch.empty(fo, fi).normal_(0.0, 1.0 / math.sqrt(fi))
+        self.w12 = nn.Parameter(pack_w12(mk(inner, d), mk(inner, d), self.ipad))
+        self.w3 = nn.Parameter(F.pad(mk(d, inner), (0, self.ipad - inner)))
+        self._register_state_dict_hook(self._export_reference_keys)
+        self._register_load_state_dict_pre_hook(self._import_reference_keys)
+
+    @staticmethod
+    def _export_reference_keys(module, state_dict, prefix, local_metadata):
+        w12, w3 = state_dict.pop(prefix + "w12"), state_dict.pop(prefix + "w3")
+        l1, l2 = unpack_w12(w12, module.inner)
+        state_dict[prefix + "l1.weight"], state_dict[prefix + "l2.weight"] = l1.contiguous(), l2.contiguous()
+        state_dict[prefix + "l3.weight"] = w3[:, :module.inner].contiguous()
+
+    def _import_reference_keys(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        names = [prefix + n for n in ("l1.weight", "l2.weight", "l3.weight")]
+        have = [n in state_dict for n in names]
+        d = self.w3.shape[0]
+        for n, ok, shape in zip(names, have, ((self.inner, d), (self.inner, d), (d, self.inner))):
+            if not ok:
+                missing_keys.append(n)
+            elif tuple(state_dict[n].shape) != shape:
+                error_msgs.append(f"size mismatch for {n}: copying a param with shape {tuple(state_dict[n].shape)} from checkpoint, the shape in current model is {shape}.")
+                have = [False] * 3
+        if have[0] and have[1]:
+            state_dict[prefix + "w12"] = pack_w12(state_dict[names[0]], state_dict[names[1]], self.ipad)
+        else:
+            state_dict[prefix + "w12"] = self.w12.data         # reported above under the reference's own key names
+        state_dict[prefix + "w3"] = F.pad(state_dict[names[2]], (0, self.ipad - self.inner)) if have[2] else self.w3.data
+        for n in names:
+            state_dict.pop(n, None)
 
 
 class _HyenaFilter(nn.Module):
@@ -213,14 +262,8 @@ class StripedHyena(nn.Module):
                 raise _lib.EvoError(f"parameter {name} is on {p.device}, expected {dev}")
         packed = {}
         for i, blk in enumerate(self.blocks):
-            inner = blk.mlp.inner
-            ipad = _round_up(inner, 128)
-            with torch.no_grad():
-                l1 = F.pad(blk.mlp.l1.weight.data, (0, 0, 0, ipad - inner)).view(ipad // 128, 1, 128, -1)
-                l2 = F.pad(blk.mlp.l2.weight.data, (0, 0, 0, ipad - inner)).view(ipad // 128, 1, 128, -1)
-                w12 = torch.cat([l1, l2], dim=1).reshape(2 * ipad, -1).contiguous()       # [l1 | l2] per 256-row tile
-                w3 = F.pad(blk.mlp.l3.weight.data, (0, ipad - inner)).contiguous()          # zero K-padding
-            packed[i] = {"w12": w12, "w3": w3, "ipad": ipad}
+            # the MLP parameters already live in the GEMM layouts (see _GatedMLP): nothing is copied here
+            packed[i] = {"w12": blk.mlp.w12.data, "w3": blk.mlp.w3.data, "ipad": blk.mlp.ipad}
         hd = self.config.hidden_size // self.config.num_attention_heads
         base = self.config.get("rotary_emb_base") or 10000
         # flash_attn keeps the checkpoint's inv_freq buffer when it is fp32 and recomputes it in fp32 otherwise

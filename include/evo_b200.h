@@ -223,6 +223,13 @@ int evo_advance_counters(int64_t* a, int64_t* b, int64_t delta, void* stream);
 int evo_logprobs(const void* logits, const int64_t* targets, float* out, int64_t rows, int V, void* stream);
 
 
+/* ---- batch front-end: evo/scoring.py:9-33 prepare_batch on the device ----
+ * bytes: the sequences' raw bytes back to back (uint8, device); offsets (B+1) int64 (device): sequence b is
+ * bytes[offsets[b] : offsets[b+1]].  ids_out (B, width) int32/int64 = [bos_id if prepend_bos] + bytes + pad_id ...
+ * (CharLevelTokenizer.tokenize is the identity on bytes, evo/tokenizer.py:41).  width >= prepend_bos + max length. */
+int evo_tokenize_pad(const void* bytes, const int64_t* offsets, void* ids_out, int ids_are_i64, int B, int64_t width,
+                     int prepend_bos, int bos_id, int pad_id, void* stream);
+
 /* ---- fused scoring head: unembed (tied embedding, N = vocab) + log_softmax + gather + entropy in one pass; the
  * (rows, V) logits never reach HBM (evo/scoring.py:36-59 logits_to_logprobs, :119-121 positional_entropies).
  * x (M, K) bf16 = final-norm output; W (V, K) bf16; targets (M) int64 (-1 = none -> logprob 0) or NULL.

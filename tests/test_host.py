@@ -1,14 +1,18 @@
 """Host-side logic that needs no GPU: tokenizer, batching, scoring math, sampling, config,
 the StripedHyena parameter tree / strict loading, and the generation loop's state protocol
 (driven with a CPU stand-in model)."""
+import json
+
 import numpy as np
 import pytest
 import torch
+import yaml
 
 import evo_b200
 from evo_b200 import CharLevelTokenizer, logits_to_logprobs, prepare_batch
 from evo_b200.configs import MODEL_NAMES, get_config
 from evo_b200.generation import Generator
+from evo_b200.models import load_checkpoint
 from evo_b200.stripedhyena import StripedHyena, dotdict, sample
 from oracle import stripedhyena_oracle as O
 
@@ -323,3 +327,99 @@ def test_config_path_resolution_matches_the_reference(tmp_path):
         _resolve_config("evo-1-8k-base", str(tmp_path / "typo.yml"))
     with pytest.raises(FileNotFoundError):
         _resolve_config("evo-1-8k-base", "elsewhere/evo-1-8k-base_inference.yml")
+
+
+def _write_sharded_checkpoint(tmp_path, cfg, seed=9, drop=("unembed.weight",), fp32_keys=()):
+    from safetensors.torch import save_file
+    sd = O.random_state_dict(cfg, seed=seed)
+    for k in drop:
+        sd.pop(k)
+    names = sorted(sd)
+    cut = len(names) // 2
+    shards = {"model-00001-of-00002.safetensors": names[:cut], "model-00002-of-00002.safetensors": names[cut:]}
+    weight_map = {}
+    for fname, keys in shards.items():
+        save_file({"backbone." + k: (sd[k].float() if k in fp32_keys else sd[k]).contiguous() for k in keys}, str(tmp_path / fname))
+        weight_map.update({"backbone." + k: fname for k in keys})
+    (tmp_path / "model.safetensors.index.json").write_text(json.dumps({"weight_map": weight_map}))
+    cfg_path = tmp_path / "tiny.yml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    return sd, names, str(cfg_path)
+
+
+def test_streaming_ingest_equals_host_state_dict_path(tmp_path):
+    """evo_b200/ingest.py (mmap -> staging -> in-place cast / pack) vs the reference's sequence (load_file -> strict
+    load_state_dict -> bf16): identical state dicts, including fp32-on-disk tensors cast on arrival, the tied unembed, the
+    MLP weights packed into w12 / w3 with exact zero padding, and strict-mode failures."""
+    from evo_b200.ingest import iter_safetensors, shard_files
+    cfg = O.tiny_config(num_layers=3, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    fp32_on_disk = ("blocks.0.mlp.l1.weight", "blocks.2.projections.weight", "norm.scale")
+    sd, names, cfg_path = _write_sharded_checkpoint(tmp_path, cfg, fp32_keys=fp32_on_disk)
+    a = load_checkpoint("evo-1-8k-base", config_path=cfg_path, model_dir=str(tmp_path), streaming=True)
+    b = load_checkpoint("evo-1-8k-base", config_path=cfg_path, model_dir=str(tmp_path), streaming=False)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert set(sa) == set(sb) == set(O.state_dict_spec(cfg))
+    for k in sa:
+        assert sa[k].dtype == sb[k].dtype and torch.equal(sa[k], sb[k]), k
+    assert a.ingest_stats["tensors"] == len(sa)                       # every key incl. the tied unembed was accounted for
+    mlp = a.blocks[0].mlp
+    assert torch.equal(mlp.w12, b.blocks[0].mlp.w12) and torch.equal(mlp.w3, b.blocks[0].mlp.w3)
+    assert mlp.w3[:, mlp.inner:].abs().sum() == 0
+    g = mlp.w12.view(mlp.ipad // 128, 2, 128, -1)
+    assert g[:, 0].reshape(mlp.ipad, -1)[mlp.inner:].abs().sum() == 0 and g[:, 1].reshape(mlp.ipad, -1)[mlp.inner:].abs().sum() == 0
+    # the raw reader sees what safetensors wrote
+    seen = {n: (dt, shape) for f in shard_files(str(tmp_path)) for n, dt, shape, raw in iter_safetensors(f)}
+    assert set(seen) == {"backbone." + k for k in names}
+    assert seen["backbone.norm.scale"][0] == torch.float32 and seen["backbone.blocks.1.inner_mha_cls.Wqkv.weight"][0] == torch.bfloat16
+    # strict mode: a missing tensor, an unexpected tensor and a wrong shape all fail loudly
+    from safetensors.torch import save_file
+    for tag, edit in (("missing", lambda d: d.pop("blocks.0.mlp.l2.weight")), ("extra", lambda d: d.__setitem__("blocks.0.bogus", torch.zeros(3))),
+                      ("shape", lambda d: d.__setitem__("blocks.0.filter.D", torch.zeros(7, dtype=torch.bfloat16)))):
+        bad = tmp_path / tag
+        bad.mkdir()
+        d = {k: sd[k] for k in names}
+        edit(d)
+        save_file({"backbone." + k: v.contiguous() for k, v in d.items()}, str(bad / "model.safetensors"))
+        with pytest.raises(RuntimeError, match="Missing key|Unexpected key|size mismatch"):
+            load_checkpoint("evo-1-8k-base", config_path=cfg_path, model_dir=str(bad))
+
+
+def test_mlp_parameters_live_only_in_the_packed_layouts():
+    """No second copy of the MLP weights: the module owns w12 / w3, the reference's key names exist at the state-dict boundary only."""
+    cfg = O.tiny_config(num_layers=1, attn_layer_idxs=(), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=1)
+    m = StripedHyena(dotdict(cfg))
+    m.load_state_dict(sd, strict=True)
+    own = dict(m.blocks[0].mlp.named_parameters())
+    assert set(own) == {"w12", "w3"}
+    out = m.state_dict()
+    for k in ("l1", "l2", "l3"):
+        assert torch.equal(out[f"blocks.0.mlp.{k}.weight"], sd[f"blocks.0.mlp.{k}.weight"].float())
+    assert "blocks.0.mlp.w12" not in out
+    bad = dict(sd)
+    bad.pop("blocks.0.mlp.l3.weight")
+    with pytest.raises(RuntimeError, match="mlp.l3.weight"):
+        StripedHyena(dotdict(cfg)).load_state_dict(bad, strict=True)
+
+
+def test_frontend_fasta_reader_and_length_buckets(tmp_path):
+    from evo_b200.frontend import length_buckets, read_fasta, read_prompts_csv
+    fa = tmp_path / "x.fasta"
+    fa.write_text(">s1 first\nACGT\nAC\n\n>s2\nTTTT\n>s3\nG\n")
+    names, seqs = read_fasta(str(fa))
+    assert names == ["s1", "s2", "s3"] and seqs == ["ACGTAC", "TTTT", "G"]
+    csvf = tmp_path / "p.csv"
+    csvf.write_text("prompt,other\nACGT,1\nGG,2\n")
+    assert read_prompts_csv(str(csvf)) == ["ACGT", "GG"]
+    seqs = ["A" * n for n in (5, 9, 5, 5, 100, 9, 5, 101, 7)]
+    exact = length_buckets(seqs, batch_size=3, mode="exact")
+    assert exact == [[0, 2, 3], [6], [1, 5], [4], [7], [8]]            # read_prompts' grouping (semantic_design.py:82-100)
+    assert all(len({len(seqs[i]) for i in b}) == 1 for b in exact)
+    srt = length_buckets(seqs, batch_size=4, mode="sorted", max_tokens=250, max_waste=0.25)
+    assert sorted(i for b in srt for i in b) == list(range(len(seqs)))
+    for b in srt:
+        width = max(len(seqs[i]) for i in b)
+        assert len(b) <= 4 and (len(b) == 1 or width * len(b) <= 250)
+        assert 1.0 - sum(len(seqs[i]) for i in b) / (width * len(b)) <= 0.25 + 1e-9
+    with pytest.raises(ValueError):
+        length_buckets(seqs, mode="nope")
