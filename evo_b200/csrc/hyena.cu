@@ -294,7 +294,9 @@ int pick_segments(const evo_hyena_params* p) {
   long long blocks = (long long)((p->D + per_cta - 1) / per_cta) * p->B;
   int sms = device_sm_count();
   if (blocks * 5 >= sms * 3 || L < 1024) return 1;
-  long long want = (sms + blocks - 1) / blocks;
+  // ONE wave: the largest segment count whose grid still fits the SMs (16 channel blocks x 9 segments = 144 CTAs on 148 SMs;
+  // rounding up to 10 gave 160 CTAs = two waves: 0.52 ms against 0.36 ms at B = 1, L = 16384, profiles/r02_hyena_micro_call2.jsonl)
+  long long want = std::max<long long>(1, sms / blocks);
   long long max_by_len = std::max<long long>(1, L / 512);
   return (int)std::max<long long>(1, std::min<long long>(std::min<long long>(want, max_by_len), 64));
 }

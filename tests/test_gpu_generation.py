@@ -73,7 +73,7 @@ def host_pipeline_probs(row, top_k, top_p, temperature):
     return torch.softmax(lt.float(), -1)[0]
 
 
-@pytest.mark.parametrize("top_k,top_p,temperature", [(4, 1.0, 1.0), (50, 0.7, 1.0), (8, 0.9, 1.25), (0, 0.5, 1.0), (0, 1.0, 1.3), (512, 0.0, 1.0)])
+@pytest.mark.parametrize("top_k,top_p,temperature", [(4, 1.0, 1.0), (50, 0.73, 1.0), (8, 0.9, 1.25), (0, 0.5, 1.0), (0, 1.0, 1.3), (512, 0.0, 1.0)])
 def test_sampler_distribution_matches_host_pipeline(top_k, top_p, temperature):
     torch.manual_seed(3)
     row = torch.randn(512).bfloat16()
@@ -87,7 +87,8 @@ def test_sampler_distribution_matches_host_pipeline(top_k, top_p, temperature):
     outside = got[~support].sum().item()
     assert outside <= 2e-3, outside
     tv = 0.5 * (got - want).abs().sum().item()
-    assert tv <= 0.02, tv
+    noise = 0.5 * 0.8 * torch.sqrt(want * (1 - want) / N).sum().item()      # E|binomial deviation| summed over the support
+    assert tv <= 2.0 * noise + 0.01, (tv, noise)
     assert int(support.sum()) >= 2                       # the case really samples
     # a second seed gives different draws, the same seed the same draws
     assert torch.equal(draws, dev_sample(row[None].expand(N, -1), top_k, top_p, temperature, seed=12345))

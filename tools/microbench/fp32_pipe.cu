@@ -37,6 +37,9 @@ __global__ void k(float* out, long long* cyc, const float* __restrict__ in) {
       else if (MODE == 4) { unsigned long long &A = *(unsigned long long*)&acc[i], &X = *(unsigned long long*)&b[i];
                             asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(A) : "l"(X)); }
       else if (MODE == 5) { asm volatile("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(cu[i]) : "r"(au[i]), "r"(bu[i])); }
+      else if (MODE == 8) { asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(cu[i]) : "f"(acc[i].x), "f"(acc[i].y)); acc[i].x = __uint_as_float(cu[i]); }
+      else if (MODE == 9) { asm volatile("shfl.sync.bfly.b32 %0, %0, 16, 0x1f, 0xffffffff;" : "+r"(cu[i])); }
+      else if (MODE == 10) { asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(cu[i]) : "r"(au[i])); }
       else if (MODE == 6) { unsigned long long &A = *(unsigned long long*)&acc[i], &X = *(unsigned long long*)&a[i], &Y = *(unsigned long long*)&b[i];
                             asm volatile("fma.rn.f32x2 %0, %1, %0, %2;" : "+l"(A) : "l"(X), "l"(Y)); }
     }
@@ -67,7 +70,7 @@ template <int MODE> void run(const char* name) {
 }
 
 int main() {
-  run<0>("FFMA r,r,r"); run<7>("FFMA shared-a"); run<1>("FFMA2 r,r,r"); run<2>("FFMA2 shared-a"); run<6>("FFMA2 acc=a*acc+b"); run<3>("FMUL2"); run<4>("FADD2"); run<5>("HFMA2.BF16");
+  run<0>("FFMA r,r,r"); run<7>("FFMA shared-a"); run<1>("FFMA2 r,r,r"); run<2>("FFMA2 shared-a"); run<6>("FFMA2 acc=a*acc+b"); run<3>("FMUL2"); run<4>("FADD2"); run<5>("HFMA2.BF16"); run<8>("F2FP.BF16.PACK + MOV"); run<9>("SHFL.BFLY"); run<10>("PRMT");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
