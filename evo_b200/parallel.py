@@ -157,8 +157,8 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 model._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
                 pos0 = rank * Lr
                 cos, sin = model._rope_tables(pos0 + Lr, dev)
-                check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + pos0 * (hd // 2) * 2), C.c_void_p(sin.data_ptr() + pos0 * (hd // 2) * 2),
-                                        B, Lr, H, hd, stream()), "evo_rotary_qk")
+                model._record("rotary", 8.0 * M * d, lambda: check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + pos0 * (hd // 2) * 2), C.c_void_p(sin.data_ptr() + pos0 * (hd // 2) * 2),
+                                                                    B, Lr, H, hd, stream()), "evo_rotary_qk"))
                 ctx = xn
                 _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, stream)
                 since_sync = 0           # the all-to-all is a global synchronisation point

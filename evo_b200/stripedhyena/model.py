@@ -320,8 +320,8 @@ class StripedHyena(nn.Module):
         self._record(f"gemm/{N}x{K}/e{epi}/streamk", 2.0 * M * N * K, lambda: check(lib.evo_gemm_smallm(C.byref(p), self._stream()), "evo_gemm_smallm"))
 
     def _rmsnorm(self, x, scale, out, rows):
-        check(_lib.lib().evo_rmsnorm(ptr(x), ptr(scale), ptr(out), rows, self.config.hidden_size,
-                                     float(self.config.eps), self._stream()), "evo_rmsnorm")
+        self._record("rmsnorm", 4.0 * rows * self.config.hidden_size, lambda: check(_lib.lib().evo_rmsnorm(
+            ptr(x), ptr(scale), ptr(out), rows, self.config.hidden_size, float(self.config.eps), self._stream()), "evo_rmsnorm"))
 
     def _rope_tables(self, n_pos, dev):
         if self._rope is None or self._rope[0].shape[0] < n_pos:
@@ -409,8 +409,8 @@ class StripedHyena(nn.Module):
         off = int(ip.seqlen_offset) if ip is not None else 0
         cos, sin = self._rope_tables(off + L, dev)
         hd2 = hd // 2
-        check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + off * hd2 * 2), C.c_void_p(sin.data_ptr() + off * hd2 * 2),
-                                B, L, H, hd, self._stream()), "evo_rotary_qk")
+        self._record("rotary", 8.0 * M * d, lambda: check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + off * hd2 * 2), C.c_void_p(sin.data_ptr() + off * hd2 * 2),
+                                                                   B, L, H, hd, self._stream()), "evo_rotary_qk"))
         ctx = xn  # reuse
         ap = AttnParams(out=ctx.data_ptr(), B=B, Lq=L, H=H, hd=hd, q_pos0=off, softmax_scale=1.0 / math.sqrt(hd))
         ap.q, ap.q_tok_stride, ap.q_batch_stride = qkv.data_ptr(), 3 * d, L * 3 * d
