@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libevo_b200.so")
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_RESID, EPI_RESID, EPI_GELU_GATE = range(5)
+EPI_BIAS_ROPE = 6
 
 
 class EvoError(RuntimeError):
@@ -20,7 +21,8 @@ class EvoError(RuntimeError):
 class GemmParams(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int64),
                 ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
-                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("epilogue", C.c_int), ("variant", C.c_int)]
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("epilogue", C.c_int), ("variant", C.c_int),
+                ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_L", C.c_int64), ("rope_cols", C.c_int64)]
 
 
 class GemmSmallMParams(C.Structure):

@@ -57,12 +57,14 @@ struct GemmArgs {
   int m_blocks, n_blocks, group_m;
   int b_tiled;           // small-M tile only: W is tile-major [N/64][K/64][64][64] (contiguous 8 KB tiles: every DRAM page opened is fully used)
   int a_rows, n_stages, ksub;  // small-M tile only: rows of A staged per k-block, ring depth, 64-column k-blocks per ring stage
+  const bf16* rope_cos; const bf16* rope_sin;   // EVO_EPI_BIAS_ROPE: (positions, 64) bf16 tables, row l = position of token row l
+  long long rope_L, rope_cols;                  //   rows repeat with period rope_L (tokens per sequence); columns < rope_cols (q and k) are rotated
   const long long* targets;   // EPI_LSE only: (M) target token per row (-1: none)
   float4* part;               // EPI_LSE only: (M, n_blocks) per-row partial statistics {max, sum e^(x-max), sum e^(x-max) x, target logit}
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
 
-constexpr int EPI_LSE = 5;     // internal: scoring epilogue (evo_unembed_score); no C is written
+constexpr int EPI_LSE = 5;     // internal: scoring epilogue (evo_unembed_score); no C is written (EVO_EPI_BIAS_ROPE is 6)
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -124,6 +126,52 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& g, long long row, in
   uint4* dst = reinterpret_cast<uint4*>(g.C + row * g.ldc + col);
 #pragma unroll
   for (int q = 0; q < 4; ++q) dst[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
+}
+
+// EVO_EPI_BIAS_ROPE: columns [col, col+32) and [col+64, col+96) of one 128-wide head: x = bf16(acc + bias) (the reference's qkv
+// tensor), then the NeoX rotation with the token's cos/sin row in fp32, one rounding on store -- the arithmetic of
+// rotary_qk_kernel (elementwise.cu), which is flash_attn's apply_rotary (layers/rotary.py:382-416, mha.py:648).
+__device__ __forceinline__ void store_rope_pair(const GemmArgs& g, long long row, int col, long long l, int c, bool rotate,
+                                                const uint32_t (&acc1)[32], const uint32_t (&acc2)[32]) {
+  float v1[32], v2[32];
+  const uint4* b1 = reinterpret_cast<const uint4*>(g.bias + col);
+  const uint4* b2 = reinterpret_cast<const uint4*>(g.bias + col + 64);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 x = __ldg(b1 + q), y = __ldg(b2 + q);
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(&x);
+    const uint32_t* yw = reinterpret_cast<const uint32_t*>(&y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v1[q * 8 + 2 * j] = rbf(__uint_as_float(acc1[q * 8 + 2 * j]) + bf_lo(xw[j])); v1[q * 8 + 2 * j + 1] = rbf(__uint_as_float(acc1[q * 8 + 2 * j + 1]) + bf_hi(xw[j]));
+      v2[q * 8 + 2 * j] = rbf(__uint_as_float(acc2[q * 8 + 2 * j]) + bf_lo(yw[j])); v2[q * 8 + 2 * j + 1] = rbf(__uint_as_float(acc2[q * 8 + 2 * j + 1]) + bf_hi(yw[j]));
+    }
+  }
+  uint32_t o1[16], o2[16];
+  if (rotate) {
+    const uint4* cp = reinterpret_cast<const uint4*>(g.rope_cos + l * 64 + c);
+    const uint4* sp = reinterpret_cast<const uint4*>(g.rope_sin + l * 64 + c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 cv = __ldg(cp + q), sv = __ldg(sp + q);
+      const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cv);
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = q * 8 + 2 * j;
+        const float cl = bf_lo(cw[j]), ch = bf_hi(cw[j]), sl = bf_lo(sw[j]), sh = bf_hi(sw[j]);
+        o1[q * 4 + j] = pack_bf16(v1[e] * cl - v2[e] * sl, v1[e + 1] * ch - v2[e + 1] * sh);
+        o2[q * 4 + j] = pack_bf16(v1[e] * sl + v2[e] * cl, v1[e + 1] * sh + v2[e + 1] * ch);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { o1[j] = pack_bf16(v1[2 * j], v1[2 * j + 1]); o2[j] = pack_bf16(v2[2 * j], v2[2 * j + 1]); }
+  }
+  uint4* d1 = reinterpret_cast<uint4*>(g.C + row * g.ldc + col);
+  uint4* d2 = reinterpret_cast<uint4*>(g.C + row * g.ldc + col + 64);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { d1[q] = make_uint4(o1[4 * q], o1[4 * q + 1], o1[4 * q + 2], o1[4 * q + 3]); d2[q] = make_uint4(o2[4 * q], o2[4 * q + 1], o2[4 * q + 2], o2[4 * q + 3]); }
 }
 
 template <int CG, int EPI, int BN>
@@ -260,6 +308,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (row < g.M) g.part[row * g.n_blocks + n_blk] = make_float4(m_run, s_run, w_run, t_logit);
+      } else if constexpr (EPI == EVO_EPI_BIAS_ROPE && BN == BN_BIG) {
+        const bool rotate = (long long)n_blk * BN < g.rope_cols;
+        const long long l = row < g.M ? row % g.rope_L : 0;
+#pragma unroll 1
+        for (int hc = 0; hc < BN; hc += 128) {
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t r1[32], r2[32];
+            tmem_ld_32x32(t0 + hc + c, r1);
+            tmem_ld_32x32(t0 + hc + 64 + c, r2);
+            tmem_ld_wait();
+            if (row < g.M) store_rope_pair(g, row, n_blk * BN + hc + c, l, c, rotate, r1, r2);
+          }
+        }
       } else if constexpr (EPI == EVO_EPI_GELU_GATE && BN == BN_BIG) {
 #pragma unroll 1
         for (int c = 0; c < BN / 2; c += 32) {
@@ -310,6 +372,7 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
   g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.targets = targets; g.part = part;
+  g.rope_cos = (const bf16*)p->rope_cos; g.rope_sin = (const bf16*)p->rope_sin; g.rope_L = p->rope_L > 0 ? p->rope_L : 1; g.rope_cols = p->rope_cols;
   g.a_rows = a_rows;
   g.b_tiled = b_tiled;
   // small tile: two 64-column k-blocks per barrier round when K allows (halves the issue thread's serial rounds)
@@ -365,6 +428,9 @@ int dispatch_epi(const evo_gemm_params* p, cudaStream_t st) {
     case EVO_EPI_BIAS: return launch<CG, EVO_EPI_BIAS, BN>(p, st);
     case EVO_EPI_BIAS_RESID: return launch<CG, EVO_EPI_BIAS_RESID, BN>(p, st);
     case EVO_EPI_RESID: return launch<CG, EVO_EPI_RESID, BN>(p, st);
+    case EVO_EPI_BIAS_ROPE:
+      if constexpr (BN == BN_BIG) return launch<CG, EVO_EPI_BIAS_ROPE, BN>(p, st);
+      else { set_error("evo_gemm: the rotary epilogue is not available on the small-M tile (variant 2)"); return -1; }
     case EVO_EPI_GELU_GATE:
       if constexpr (BN == BN_BIG) return launch<CG, EVO_EPI_GELU_GATE, BN>(p, st);
       else { set_error("evo_gemm: the GELU-gate epilogue is not available on the small-M tile (variant 2)"); return -1; }
@@ -381,7 +447,10 @@ extern "C" int evo_gemm(const evo_gemm_params* p, void* stream) {
   EVO_REQUIRE(p->N % BN_BIG == 0, "evo_gemm: N (%lld) must be a multiple of %d (pack weights at load time)", (long long)p->N, BN_BIG);
   EVO_REQUIRE(p->lda % 8 == 0 && p->ldc % 8 == 0, "evo_gemm: lda/ldc must be multiples of 8 elements");
   EVO_REQUIRE(((uintptr_t)p->A % 16) == 0 && ((uintptr_t)p->W % 16) == 0 && ((uintptr_t)p->C % 16) == 0, "evo_gemm: pointers must be 16-byte aligned");
-  if (p->epilogue == EVO_EPI_BIAS || p->epilogue == EVO_EPI_BIAS_RESID) EVO_REQUIRE(p->bias != nullptr, "evo_gemm: bias epilogue without bias");
+  if (p->epilogue == EVO_EPI_BIAS || p->epilogue == EVO_EPI_BIAS_RESID || p->epilogue == EVO_EPI_BIAS_ROPE) EVO_REQUIRE(p->bias != nullptr, "evo_gemm: bias epilogue without bias");
+  if (p->epilogue == EVO_EPI_BIAS_ROPE)
+    EVO_REQUIRE(p->rope_cos && p->rope_sin && p->rope_L > 0 && p->rope_cols % 128 == 0 && p->rope_cols <= p->N && ((uintptr_t)p->rope_cos % 16) == 0 && ((uintptr_t)p->rope_sin % 16) == 0,
+                "evo_gemm: rotary epilogue needs 16-byte aligned cos/sin tables, rope_L > 0 and rope_cols a multiple of the head width (128)");
   if (p->epilogue == EVO_EPI_RESID || p->epilogue == EVO_EPI_BIAS_RESID)
     EVO_REQUIRE(p->residual != nullptr && p->ldr % 8 == 0 && ((uintptr_t)p->residual % 16) == 0, "evo_gemm: residual epilogue without a valid residual");
   if (p->M == 0) return 0;

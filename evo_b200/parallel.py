@@ -25,7 +25,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_BIAS_RESID, EPI_NONE, EPI_RESID, AttnParams, HyenaParams, check, ptr
+from ._lib import EPI_BIAS, EPI_BIAS_RESID, EPI_BIAS_ROPE, EPI_NONE, EPI_RESID, AttnParams, HyenaParams, check, ptr
 
 
 def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
@@ -154,11 +154,14 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
             if i in model._attn_idxs:
                 mha = blk.inner_mha_cls
                 qkv = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
-                model._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
                 pos0 = rank * Lr
                 cos, sin = model._rope_tables(pos0 + Lr, dev)
-                model._record("rotary", 8.0 * M * d, lambda: check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + pos0 * (hd // 2) * 2), C.c_void_p(sin.data_ptr() + pos0 * (hd // 2) * 2),
-                                                                    B, Lr, H, hd, stream()), "evo_rotary_qk"))
+                cos_p, sin_p = cos.data_ptr() + pos0 * (hd // 2) * 2, sin.data_ptr() + pos0 * (hd // 2) * 2
+                if model.fused_rope and mha.Wqkv.bias is not None and hd == 128 and model.gemm_variant in (0, 1):
+                    model._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS_ROPE, bias=mha.Wqkv.bias, rope=(cos_p, sin_p, Lr, 2 * d))
+                else:
+                    model._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
+                    model._record("rotary", 8.0 * M * d, lambda: check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos_p), C.c_void_p(sin_p), B, Lr, H, hd, stream()), "evo_rotary_qk"))
                 ctx = xn
                 _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, stream)
                 since_sync = 0           # the all-to-all is a global synchronisation point

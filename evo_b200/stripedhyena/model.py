@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_GELU_GATE, EPI_NONE, EPI_RESID, AttnParams, GemmParams, GemmSmallMParams,
+from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_BIAS_ROPE, EPI_GELU_GATE, EPI_NONE, EPI_RESID, AttnParams, GemmParams, GemmSmallMParams,
                     HyenaParams, check, ptr)
 from .cache import InferenceParams, RecurrentInferenceParams
 
@@ -201,6 +201,8 @@ class StripedHyena(nn.Module):
         self.gemm_variant_gate = GEMM_VARIANT_GATE
         self.attn_variant = ATTN_VARIANT
         self.decode_graph = os.environ.get("EVO_B200_DECODE_GRAPH", "1") != "0"
+        # rotary embedding inside the Wqkv GEMM's epilogue (EVO_EPI_BIAS_ROPE) instead of a separate pass over qkv; "0" = separate evo_rotary_qk
+        self.fused_rope = os.environ.get("EVO_B200_FUSED_ROPE", "1") != "0"
         # tile-major weight copies for decode (GEMM variant 3): validated bit-identical but no faster on B200 (6.57 vs 6.65 ms/step:
         # the small-M GEMM is bound by bytes in flight per CTA and by too few CTAs at N=4096, not by DRAM page locality), so off
         self.decode_tiled = os.environ.get("EVO_B200_DECODE_TILED", "0") != "0"
@@ -295,13 +297,16 @@ class StripedHyena(nn.Module):
         e1.record()
         self._prof.append((kind, work, e0, e1))
 
-    def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None, variant=None):
+    def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None, variant=None, rope=None):
+        """rope = (cos_ptr, sin_ptr, tokens_per_sequence, rotated_columns) for EPI_BIAS_ROPE."""
         if variant is None:
             variant = self.gemm_variant_gate if epi == EPI_GELU_GATE else self.gemm_variant
         p = GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=ldc or N,
                        bias=bias.data_ptr() if bias is not None else None,
                        residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
                        M=M, N=N, K=K, epilogue=epi, variant=variant)
+        if rope is not None:
+            p.rope_cos, p.rope_sin, p.rope_L, p.rope_cols = rope
         self._record(f"gemm/{N}x{K}/e{epi}/v{variant}", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
 
     def _gemm_smallm(self, a, w, out, M, N, K, epi, bias=None, resid=None):
@@ -405,12 +410,16 @@ class StripedHyena(nn.Module):
         xn = torch.empty_like(u)
         self._rmsnorm(u, blk.pre_norm.scale, xn, M)
         qkv = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
-        self._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
         off = int(ip.seqlen_offset) if ip is not None else 0
         cos, sin = self._rope_tables(off + L, dev)
         hd2 = hd // 2
-        self._record("rotary", 8.0 * M * d, lambda: check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos.data_ptr() + off * hd2 * 2), C.c_void_p(sin.data_ptr() + off * hd2 * 2),
-                                                                   B, L, H, hd, self._stream()), "evo_rotary_qk"))
+        cos_p, sin_p = cos.data_ptr() + off * hd2 * 2, sin.data_ptr() + off * hd2 * 2
+        if self.fused_rope and mha.Wqkv.bias is not None and hd == 128 and self.gemm_variant in (0, 1):
+            # rotary applied in the projection's epilogue, where flash_attn's MHA applies it (mha.py:635-648): no second pass over qkv
+            self._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS_ROPE, bias=mha.Wqkv.bias, rope=(cos_p, sin_p, L, 2 * d))
+        else:
+            self._gemm(xn, mha.Wqkv.weight, qkv, M, 3 * d, d, EPI_BIAS if mha.Wqkv.bias is not None else EPI_NONE, bias=mha.Wqkv.bias)
+            self._record("rotary", 8.0 * M * d, lambda: check(lib.evo_rotary_qk(ptr(qkv), C.c_void_p(cos_p), C.c_void_p(sin_p), B, L, H, hd, self._stream()), "evo_rotary_qk"))
         ctx = xn  # reuse
         ap = AttnParams(out=ctx.data_ptr(), B=B, Lq=L, H=H, hd=hd, q_pos0=off, softmax_scale=1.0 / math.sqrt(hd))
         ap.q, ap.q_tok_stride, ap.q_batch_stride = qkv.data_ptr(), 3 * d, L * 3 * d

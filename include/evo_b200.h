@@ -55,8 +55,13 @@ enum {
   EVO_EPI_BIAS = 1,       /* C = bf16(acc + bias[n])                nn.Linear(bias=True) */
   EVO_EPI_BIAS_RESID = 2, /* C = bf16(bf16(acc + bias[n]) + R[m,n]) out_filter_dense(z)+u, out_proj(ctx)+u */
   EVO_EPI_RESID = 3,      /* C = bf16(bf16(acc) + R[m,n])           l3(...) + u           */
-  EVO_EPI_GELU_GATE = 4   /* W rows interleaved in 128-row groups [l1 | l2]; C[M,N/2] =
+  EVO_EPI_GELU_GATE = 4,  /* W rows interleaved in 128-row groups [l1 | l2]; C[M,N/2] =
                              bf16(gelu(bf16(acc1)) * bf16(acc2))    act(l1 x) * l2 x      */
+  EVO_EPI_BIAS_ROPE = 6   /* Wqkv projection with the rotary embedding applied where flash_attn applies it
+                             (MHA.forward, mha.py:635-648): x = bf16(acc + bias[n]); columns n < rope_cols (q and k,
+                             heads of 128) are rotated NeoX-style with the cos/sin row of the token's position
+                             (row m -> table row m % rope_L; the caller offsets the tables by the first position),
+                             fp32 arithmetic, one rounding on store -- evo_rotary_qk's result without a second pass */
 };
 typedef struct {
   const void* A; int64_t lda;
@@ -68,6 +73,9 @@ typedef struct {
   int epilogue;
   int variant;                   /* 0 = 2-CTA 256x256 tiles; 1 = 1-CTA 128x256 tiles; 2 = 1-CTA 128x64 weight-streaming tiles (small M);
                                     3 = like 2 with W given tile-major: (N/64, K/64, 64, 64), i.e. W.view(N/64,64,K/64,64).permute(0,2,1,3) */
+  const void* rope_cos; const void* rope_sin;   /* EVO_EPI_BIAS_ROPE: (positions, 64) bf16 tables (evo_rope_tables) */
+  int64_t rope_L;                /* tokens per sequence: row m uses table row m % rope_L */
+  int64_t rope_cols;             /* columns [0, rope_cols) are rotated (2*H*128 for a qkv projection), the rest only get the bias */
 } evo_gemm_params;
 int evo_gemm(const evo_gemm_params* p, void* stream);
 /* Decode-step linear layer (M <= 64 rows): the same C = epilogue(A . W^T) with the same rounding points, as a

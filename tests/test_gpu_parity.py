@@ -106,6 +106,41 @@ def test_rope_tables_and_rotary(scaling):
     assert torch.equal(out[:, :, 2], qkv[:, :, 2])
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("B,L,H,off", [(2, 300, 2, 0), (1, 129, 4, 77), (1, 8193, 32, 0)])
+def test_gemm_rotary_epilogue_equals_projection_then_rotary(variant, B, L, H, off):
+    """EVO_EPI_BIAS_ROPE (rotary inside the Wqkv GEMM's epilogue, where flash_attn's MHA applies it, mha.py:635-648) vs the
+    two-kernel path (bias epilogue, then evo_rotary_qk): same rounding points, so bit-identical up to fma contraction; and
+    vs the oracle's apply_rotary on the projection output."""
+    d, K, M = H * 128, 256, B * L
+    torch.manual_seed(L + H)
+    a = (torch.randn(M, K, device=DEV) * 0.7).bfloat16()
+    w = (torch.randn(3 * d, K, device=DEV) / 16).bfloat16()
+    bias = torch.randn(3 * d, device=DEV).bfloat16()
+    cos, sin = O.rotary_tables(off + L, 128, scaling_factor=16.0 if H == 4 else 1.0, dtype=torch.bfloat16)
+    cd, sd_ = cos.to(DEV), sin.to(DEV)
+    cp, sp = cd.data_ptr() + off * 64 * 2, sd_.data_ptr() + off * 64 * 2
+    two = G._gemm(a, w, M, 3 * d, K, _lib.EPI_BIAS, variant, bias=bias)
+    plain = two.clone()
+    _lib.check(_lib.lib().evo_rotary_qk(_lib.ptr(two), C.c_void_p(cp), C.c_void_p(sp), B, L, H, 128, stream()))
+    fused = torch.full((M, 3 * d), float("nan"), dtype=torch.bfloat16, device=DEV)
+    p = _lib.GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=fused.data_ptr(), ldc=3 * d, bias=bias.data_ptr(), residual=None, ldr=3 * d,
+                        M=M, N=3 * d, K=K, epilogue=_lib.EPI_BIAS_ROPE, variant=variant, rope_cos=cp, rope_sin=sp, rope_L=L, rope_cols=2 * d)
+    _lib.check(_lib.lib().evo_gemm(C.byref(p), stream()), "evo_gemm(rope)")
+    torch.cuda.synchronize()
+    assert not torch.isnan(fused.float()).any()
+    assert torch.equal(fused[:, 2 * d:], plain[:, 2 * d:])                      # v: bias only
+    assert (fused == two).float().mean().item() > 0.9999 and maxerr(fused, two) <= 2 ** -6 * max(1.0, two.float().abs().max().item())
+    qk = plain.cpu().view(B, L, 3, H, 128)
+    for which in (0, 1):
+        ref = O.apply_rotary(qk[:, :, which], cos[off:], sin[off:])
+        got = fused.cpu().view(B, L, 3, H, 128)[:, :, which]
+        assert (got == ref).float().mean() > 0.999 and maxerr(got, ref) <= 2 ** -6 * max(1.0, ref.abs().max().item())
+    bad = _lib.GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=fused.data_ptr(), ldc=3 * d, bias=bias.data_ptr(), residual=None, ldr=3 * d,
+                          M=M, N=3 * d, K=K, epilogue=_lib.EPI_BIAS_ROPE, variant=variant)                       # no tables
+    assert _lib.lib().evo_gemm(C.byref(bad), stream()) != 0
+
+
 def test_kv_append_and_logprobs():
     lib = _lib.lib()
     qkv = torch.randn(2, 5, 3, 2, 128).bfloat16()
