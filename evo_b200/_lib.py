@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libevo_b200.so")
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_RESID, EPI_RESID, EPI_GELU_GATE = range(5)
 EPI_BIAS_ROPE = 6
+EPI_HYENA_STEP = 7
 
 
 class EvoError(RuntimeError):
@@ -29,7 +30,9 @@ class GemmSmallMParams(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int64),
                 ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("epilogue", C.c_int),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("fir_state", C.c_void_p), ("state", C.c_void_p), ("fir_w", C.c_void_p), ("fir_b", C.c_void_p), ("Dskip", C.c_void_p),
+                ("poles", C.c_void_p), ("residues", C.c_void_p)]
 
 
 class HyenaParams(C.Structure):

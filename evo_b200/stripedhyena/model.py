@@ -23,8 +23,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
-from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_BIAS_ROPE, EPI_GELU_GATE, EPI_NONE, EPI_RESID, AttnParams, GemmParams, GemmSmallMParams,
-                    HyenaParams, check, ptr)
+from .._lib import (EPI_BIAS, EPI_BIAS_RESID, EPI_BIAS_ROPE, EPI_GELU_GATE, EPI_HYENA_STEP, EPI_NONE, EPI_RESID, AttnParams, GemmParams,
+                    GemmSmallMParams, HyenaParams, check, ptr)
 from .cache import InferenceParams, RecurrentInferenceParams
 
 # kernel variants (see include/evo_b200.h); overridable for experiments
@@ -210,6 +210,8 @@ class StripedHyena(nn.Module):
         self.decode_streamk = os.environ.get("EVO_B200_DECODE_STREAMK", "1") != "0"
         # programmatic dependent launch inside a decode step (evo_set_pdl): 0 off, 1 every kernel, 2 weight-streaming GEMMs only
         self.decode_pdl = int(os.environ.get("EVO_B200_DECODE_PDL", "2"))
+        # the Hyena decode step inside the in-projection GEMM's epilogue (EVO_EPI_HYENA_STEP); "0" = separate evo_hyena_step launch
+        self.decode_fused_step = os.environ.get("EVO_B200_DECODE_FUSED_STEP", "1") != "0"
         self._smallm_ws = None
         self._tiled = None   # tile-major weight copies for the weight-streaming decode GEMMs
         self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
@@ -309,19 +311,27 @@ class StripedHyena(nn.Module):
             p.rope_cos, p.rope_sin, p.rope_L, p.rope_cols = rope
         self._record(f"gemm/{N}x{K}/e{epi}/v{variant}", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
 
-    def _gemm_smallm(self, a, w, out, M, N, K, epi, bias=None, resid=None):
-        """Decode-step linear layer (M <= 64): stream-K weight-streaming kernel, gate epilogue fused."""
+    def _gemm_smallm(self, a, w, out, M, N, K, epi, bias=None, resid=None, step=None):
+        """Decode-step linear layer (M <= 64): stream-K weight-streaming kernel, gate epilogue fused.
+        step = (fir_state, state_real, filter module) for EPI_HYENA_STEP: the in-projection with the operator's decode step
+        in its epilogue (out is then y (M, N/3))."""
         lib = _lib.lib()
         need = lib.evo_gemm_smallm_workspace(M, N, K, epi)
         ws = self._smallm_ws
         if ws is None or ws.numel() < need or ws.device != a.device:
             self._decode = None      # a captured decode graph holds the old workspace address
-            ws = self._smallm_ws = torch.zeros(max(need, lib.evo_gemm_smallm_workspace(M, 256, 64, EPI_GELU_GATE)), dtype=torch.uint8, device=a.device)
-        n_out = N // 2 if epi == EPI_GELU_GATE else N
+            ws = self._smallm_ws = torch.zeros(max(need, lib.evo_gemm_smallm_workspace(M, 256, 64, EPI_GELU_GATE), lib.evo_gemm_smallm_workspace(M, 384, 64, EPI_HYENA_STEP)),
+                                               dtype=torch.uint8, device=a.device)
+        n_out = N // 2 if epi == EPI_GELU_GATE else (N // 3 if epi == EPI_HYENA_STEP else N)
         p = GemmSmallMParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=n_out,
                              bias=bias.data_ptr() if bias is not None else None,
                              residual=resid.data_ptr() if resid is not None else None, ldr=n_out,
                              M=M, N=N, K=K, epilogue=epi, workspace=ws.data_ptr(), workspace_bytes=ws.numel())
+        if step is not None:
+            fs, st, f = step
+            p.fir_state, p.state = fs.data_ptr(), st.data_ptr()
+            p.fir_w, p.fir_b, p.Dskip = f.short_filter_weight.data_ptr(), f.short_filter_bias.data_ptr(), f.D.data_ptr()
+            p.poles, p.residues = f.poles.data_ptr(), f.residues.data_ptr()
         self._record(f"gemm/{N}x{K}/e{epi}/streamk", 2.0 * M * N * K, lambda: check(lib.evo_gemm_smallm(C.byref(p), self._stream()), "evo_gemm_smallm"))
 
     def _rmsnorm(self, x, scale, out, rows):
@@ -605,12 +615,18 @@ class StripedHyena(nn.Module):
                     bias=mha.out_proj.bias, resid=u)
             else:
                 f = blk.filter
-                z = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
-                lin(xn, wsel(i, "in", blk.projections.weight), z, 3 * d, d, EPI_BIAS, bias=blk.projections.bias)
-                y = xn
-                check(lib.evo_hyena_step(ptr(z), ptr(y), ptr(hy_ip.fir_state_dict[i]), ptr(torch.view_as_real(hy_ip.state_dict[i])),
-                                         ptr(f.short_filter_weight), ptr(f.short_filter_bias), ptr(f.D), ptr(f.poles), ptr(f.residues),
-                                         B, d, cfg.state_size, H, self._stream()), "evo_hyena_step")
+                if streamk and self.decode_fused_step and hd == 128:
+                    # in-projection with engine.step_fir + step_iir in its epilogue: z never leaves the SM, one launch less per layer
+                    y = torch.empty(B, d, dtype=torch.bfloat16, device=dev)
+                    self._gemm_smallm(xn, blk.projections.weight, y, B, 3 * d, d, EPI_HYENA_STEP, bias=blk.projections.bias,
+                                      step=(hy_ip.fir_state_dict[i], torch.view_as_real(hy_ip.state_dict[i]), f))
+                else:
+                    z = torch.empty(B, 3 * d, dtype=torch.bfloat16, device=dev)
+                    lin(xn, wsel(i, "in", blk.projections.weight), z, 3 * d, d, EPI_BIAS, bias=blk.projections.bias)
+                    y = xn
+                    check(lib.evo_hyena_step(ptr(z), ptr(y), ptr(hy_ip.fir_state_dict[i]), ptr(torch.view_as_real(hy_ip.state_dict[i])),
+                                             ptr(f.short_filter_weight), ptr(f.short_filter_bias), ptr(f.D), ptr(f.poles), ptr(f.residues),
+                                             B, d, cfg.state_size, H, self._stream()), "evo_hyena_step")
                 lin(y, wsel(i, "out", blk.out_filter_dense.weight), u2, d, d, EPI_BIAS_RESID, bias=blk.out_filter_dense.bias, resid=u)
             pk = self._packed[i]
             xn2 = xn

@@ -57,6 +57,9 @@ enum {
   EVO_EPI_RESID = 3,      /* C = bf16(bf16(acc) + R[m,n])           l3(...) + u           */
   EVO_EPI_GELU_GATE = 4,  /* W rows interleaved in 128-row groups [l1 | l2]; C[M,N/2] =
                              bf16(gelu(bf16(acc1)) * bf16(acc2))    act(l1 x) * l2 x      */
+  EVO_EPI_HYENA_STEP = 7, /* evo_gemm_smallm only: the Hyena in-projection (N = 3D, bias) with the decode step of the operator
+                             (engine.step_fir + step_iir == evo_hyena_step) applied in the epilogue: a tile is one head's
+                             [x2 | x1 | v] rows, C is y (M, D); fir_state / state are updated in place; z is never stored */
   EVO_EPI_BIAS_ROPE = 6   /* Wqkv projection with the rotary embedding applied where flash_attn applies it
                              (MHA.forward, mha.py:635-648): x = bf16(acc + bias[n]); columns n < rope_cols (q and k,
                              heads of 128) are rotated NeoX-style with the cos/sin row of the token's position
@@ -93,6 +96,10 @@ typedef struct {
   int64_t M, N, K;               /* M <= 64, N % 256 == 0, K % 64 == 0 */
   int epilogue;                  /* EVO_EPI_* */
   void* workspace; size_t workspace_bytes;
+  /* EVO_EPI_HYENA_STEP only (same tensors as evo_hyena_step): */
+  void* fir_state; float* state;                 /* (M, 3D, 2) bf16, (M, D, 8, 2) fp32: in/out */
+  const void* fir_w; const void* fir_b; const void* Dskip;
+  const float* poles; const float* residues;
 } evo_gemm_smallm_params;
 size_t evo_gemm_smallm_workspace(int64_t M, int64_t N, int64_t K, int epilogue);
 int evo_gemm_smallm(const evo_gemm_smallm_params* p, void* stream);

@@ -595,6 +595,41 @@ def test_decode_streamk_pdl_paths_agree():
     assert torch.equal(b, c) and torch.equal(b, e)        # PDL and graph replay change scheduling only
 
 
+def test_decode_fused_hyena_step_epilogue_is_bit_identical():
+    """EVO_EPI_HYENA_STEP (engine.step_fir + step_iir inside the in-projection GEMM's epilogue) vs the two-launch path
+    (bias epilogue, then evo_hyena_step): logits AND the recurrent states after 40 steps, bit for bit; eager and graph replay."""
+    cfg, sd, m = _tiny()
+    torch.manual_seed(4)
+    ids = (torch.randint(0, 4, (3, 100)) * 3 + 65).to(DEV)
+
+    def run(fused, graph):
+        m.decode_fused_step, m.decode_graph, m._decode, m._loop = fused, graph, None, None
+        d = m.initialize_inference_params()
+        d["mha"].max_batch_size, d["mha"].max_seqlen = 3, 128
+        _, d = m(ids[:, :60], inference_params_dict=d)
+        d["mha"].seqlen_offset = d["hyena"].seqlen_offset = 60
+        outs = []
+        for t in range(60, 100):
+            s, d = m(ids[:, t:t + 1], inference_params_dict=d)
+            outs.append(s[:, 0].clone())
+            d["mha"].seqlen_offset += 1
+            d["hyena"].seqlen_offset += 1
+        return torch.stack(outs, 1), {k: v.clone() for k, v in d["hyena"].state_dict.items()}, {k: v.clone() for k, v in d["hyena"].fir_state_dict.items()}
+
+    saved = (m.decode_fused_step, m.decode_graph)
+    try:
+        a, sa, fa = run(False, False)
+        b, sb, fb = run(True, False)
+        c, sc, fc = run(True, True)
+    finally:
+        m.decode_fused_step, m.decode_graph = saved
+        m._decode = m._loop = None
+    assert torch.equal(a, b) and torch.equal(b, c)
+    for k in sa:
+        assert torch.equal(torch.view_as_real(sa[k]), torch.view_as_real(sb[k])) and torch.equal(torch.view_as_real(sb[k]), torch.view_as_real(sc[k]))
+        assert torch.equal(fa[k], fb[k]) and torch.equal(fb[k], fc[k])
+
+
 def test_public_api_scoring_and_generation():
     import evo_b200
     cfg, sd, m = _tiny(layers=3, attn=(1,))
