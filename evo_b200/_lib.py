@@ -23,7 +23,8 @@ class GemmParams(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("C", C.c_void_p), ("ldc", C.c_int64),
                 ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64), ("epilogue", C.c_int), ("variant", C.c_int),
-                ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_L", C.c_int64), ("rope_cols", C.c_int64)]
+                ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_L", C.c_int64), ("rope_cols", C.c_int64),
+                ("c_peers", C.c_void_p), ("n_c_peers", C.c_int), ("peer_period", C.c_int64), ("peer_inner", C.c_int64), ("peer_row0", C.c_int64)]
 
 
 class GemmSmallMParams(C.Structure):
@@ -48,7 +49,8 @@ class AttnParams(C.Structure):
                 ("q_tok_stride", C.c_int64), ("kv_tok_stride", C.c_int64),
                 ("q_batch_stride", C.c_int64), ("kv_batch_stride", C.c_int64),
                 ("B", C.c_int), ("Lq", C.c_int64), ("Lk", C.c_int64), ("H", C.c_int), ("hd", C.c_int),
-                ("q_pos0", C.c_int64), ("softmax_scale", C.c_float)]
+                ("q_pos0", C.c_int64), ("softmax_scale", C.c_float),
+                ("out_peers", C.c_void_p), ("n_out_peers", C.c_int), ("out_rows_per_peer", C.c_int64), ("out_row_stride", C.c_int64), ("out_col0", C.c_int64)]
 
 
 class ScoreParams(C.Structure):

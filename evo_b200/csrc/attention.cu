@@ -352,6 +352,7 @@ extern "C" int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* work
               "evo_attn_fwd: strides must be multiples of 8 elements");
   EVO_REQUIRE(p->q_pos0 + p->Lq <= p->Lk, "evo_attn_fwd: queries extend past the keys (q_pos0 %lld + Lq %lld > Lk %lld)",
               (long long)p->q_pos0, (long long)p->Lq, (long long)p->Lk);
+  EVO_REQUIRE(p->n_out_peers == 0 || variant == 2, "evo_attn_fwd: peer-scattered output is implemented by variant 2 only");
   if (p->Lq == 0 || p->B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmQ, tmK, tmV;

@@ -34,6 +34,7 @@ constexpr uint32_t TM_S = 0, TM_O = 256;        // + 128 * tile
 
 struct Args {
   bf16* out;
+  bf16* out_peer[8]; int n_out_peers; long long out_rows_per_peer, out_row_stride, out_col0;   // peer-scattered output (evo_attn_params)
   int B, H;
   long long Lq, Lk, q_pos0;
   float scale_log2;
@@ -244,6 +245,10 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc_fence_after();
       const float inv_l = 1.f / l;
       bf16* orow = a.out + (((long long)b * a.Lq + q0[t] + r) * a.H + h) * HD;
+      if (a.n_out_peers > 0) {
+        const long long tok = q0[t] + r, pr = tok / a.out_rows_per_peer;
+        orow = a.out_peer[pr < a.n_out_peers ? pr : 0] + (tok - pr * a.out_rows_per_peer) * a.out_row_stride + a.out_col0 + (long long)h * HD;
+      }
 #pragma unroll 1
       for (int c = 0; c < HD; c += 32) {
         uint32_t tt[32];
@@ -279,6 +284,13 @@ int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
   a.out = (bf16*)p->out; a.B = p->B; a.H = p->H; a.Lq = p->Lq; a.Lk = p->Lk; a.q_pos0 = p->q_pos0;
   a.scale_log2 = p->softmax_scale * 1.4426950408889634f;
   a.n_qblk = (int)((p->Lq + BQ - 1) / BQ);
+  a.n_out_peers = p->n_out_peers; a.out_rows_per_peer = p->out_rows_per_peer; a.out_row_stride = p->out_row_stride; a.out_col0 = p->out_col0;
+  for (int i = 0; i < 8; ++i) a.out_peer[i] = i < p->n_out_peers ? (bf16*)p->out_peers[i] : nullptr;
+  if (p->n_out_peers != 0) {
+    EVO_REQUIRE(p->n_out_peers > 0 && p->n_out_peers <= 8 && p->out_peers != nullptr && p->B == 1 && p->out_rows_per_peer > 0 &&
+                p->out_rows_per_peer * p->n_out_peers >= p->Lq && p->out_row_stride % 8 == 0 && p->out_col0 % 8 == 0,
+                "evo_attn_fwd: peer-scattered output needs B == 1, 1..8 peers covering Lq rows, 16-byte aligned strides");
+  }
   static unsigned long long done = 0;
   { int rc_ = ensure_dyn_smem(attn_pp_kernel, SMEM, done); if (rc_) return rc_; }
   dim3 grid((unsigned)((a.n_qblk + 1) / 2), p->H, p->B);

@@ -57,6 +57,9 @@ struct GemmArgs {
   int m_blocks, n_blocks, group_m;
   int b_tiled;           // small-M tile only: W is tile-major [N/64][K/64][64][64] (contiguous 8 KB tiles: every DRAM page opened is fully used)
   int a_rows, n_stages, ksub;  // small-M tile only: rows of A staged per k-block, ring depth, 64-column k-blocks per ring stage
+  // peer-scattered output (sequence-parallel Ulysses re-shard fused into the Wqkv epilogue): column n of row m goes to
+  // c_peer[(n % peer_period) / peer_inner] at [(peer_row0 + m) * ldc + (n / peer_period) * peer_inner + n % peer_inner]
+  bf16* c_peer[8]; int n_peers; int peer_period, peer_inner; long long peer_row0;
   const bf16* rope_cos; const bf16* rope_sin;   // EVO_EPI_BIAS_ROPE: (positions, 64) bf16 tables, row l = position of token row l
   long long rope_L, rope_cols;                  //   rows repeat with period rope_L (tokens per sequence); columns < rope_cols (q and k) are rotated
   const long long* targets;   // EPI_LSE only: (M) target token per row (-1: none)
@@ -80,6 +83,14 @@ __device__ __forceinline__ void tile_coords(int tile, const GemmArgs& g, int& m_
   int a = first + in % gsz, b = in / gsz;
   m_blk = g.raster_n ? b : a;
   n_blk = g.raster_n ? a : b;
+}
+
+// address of C[row, col] (col = first column of a 32-wide chunk; a chunk never straddles a head)
+__device__ __forceinline__ bf16* c_ptr(const GemmArgs& g, long long row, int col) {
+  if (g.n_peers == 0) return g.C + row * g.ldc + col;
+  const int t = col / g.peer_period, rem = col - t * g.peer_period;
+  const int p = rem / g.peer_inner;
+  return g.c_peer[p] + (g.peer_row0 + row) * g.ldc + t * g.peer_inner + (rem - p * g.peer_inner);
 }
 
 template <int EPI>
@@ -123,7 +134,7 @@ __device__ __forceinline__ void store_chunk(const GemmArgs& g, long long row, in
 #pragma unroll
     for (int j = 0; j < 16; ++j) outw[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
   }
-  uint4* dst = reinterpret_cast<uint4*>(g.C + row * g.ldc + col);
+  uint4* dst = reinterpret_cast<uint4*>(c_ptr(g, row, col));
 #pragma unroll
   for (int q = 0; q < 4; ++q) dst[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
 }
@@ -168,8 +179,8 @@ __device__ __forceinline__ void store_rope_pair(const GemmArgs& g, long long row
 #pragma unroll
     for (int j = 0; j < 16; ++j) { o1[j] = pack_bf16(v1[2 * j], v1[2 * j + 1]); o2[j] = pack_bf16(v2[2 * j], v2[2 * j + 1]); }
   }
-  uint4* d1 = reinterpret_cast<uint4*>(g.C + row * g.ldc + col);
-  uint4* d2 = reinterpret_cast<uint4*>(g.C + row * g.ldc + col + 64);
+  uint4* d1 = reinterpret_cast<uint4*>(c_ptr(g, row, col));
+  uint4* d2 = reinterpret_cast<uint4*>(c_ptr(g, row, col + 64));
 #pragma unroll
   for (int q = 0; q < 4; ++q) { d1[q] = make_uint4(o1[4 * q], o1[4 * q + 1], o1[4 * q + 2], o1[4 * q + 3]); d2[q] = make_uint4(o2[4 * q], o2[4 * q + 1], o2[4 * q + 2], o2[4 * q + 3]); }
 }
@@ -372,6 +383,8 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
   g.C = (bf16*)p->C; g.ldc = p->ldc; g.bias = (const bf16*)p->bias; g.resid = (const bf16*)p->residual; g.ldr = p->ldr;
   g.M = p->M; g.N = p->N; g.K = p->K;
   g.targets = targets; g.part = part;
+  g.n_peers = p->n_c_peers; g.peer_period = (int)p->peer_period; g.peer_inner = (int)p->peer_inner; g.peer_row0 = p->peer_row0;
+  for (int i = 0; i < 8; ++i) g.c_peer[i] = i < p->n_c_peers ? (bf16*)p->c_peers[i] : nullptr;
   g.rope_cos = (const bf16*)p->rope_cos; g.rope_sin = (const bf16*)p->rope_sin; g.rope_L = p->rope_L > 0 ? p->rope_L : 1; g.rope_cols = p->rope_cols;
   g.a_rows = a_rows;
   g.b_tiled = b_tiled;
@@ -453,6 +466,13 @@ extern "C" int evo_gemm(const evo_gemm_params* p, void* stream) {
                 "evo_gemm: rotary epilogue needs 16-byte aligned cos/sin tables, rope_L > 0 and rope_cols a multiple of the head width (128)");
   if (p->epilogue == EVO_EPI_RESID || p->epilogue == EVO_EPI_BIAS_RESID)
     EVO_REQUIRE(p->residual != nullptr && p->ldr % 8 == 0 && ((uintptr_t)p->residual % 16) == 0, "evo_gemm: residual epilogue without a valid residual");
+  if (p->n_c_peers != 0) {
+    EVO_REQUIRE(p->n_c_peers > 0 && p->n_c_peers <= 8 && p->c_peers != nullptr, "evo_gemm: 1..8 peer destinations");
+    EVO_REQUIRE(p->peer_inner > 0 && p->peer_inner % 128 == 0 && p->peer_period == p->peer_inner * p->n_c_peers && p->N % p->peer_period == 0,
+                "evo_gemm: peer scatter needs peer_inner %% 128 == 0, peer_period = n_peers * peer_inner, N %% peer_period == 0");
+    EVO_REQUIRE(p->epilogue == EVO_EPI_BIAS || p->epilogue == EVO_EPI_NONE || p->epilogue == EVO_EPI_BIAS_ROPE, "evo_gemm: peer scatter supports the none / bias / rotary epilogues");
+    EVO_REQUIRE(p->variant == 0 || p->variant == 1, "evo_gemm: peer scatter needs the 256-column tiles");
+  }
   if (p->M == 0) return 0;
   if (p->variant == 2 || p->variant == 3) return dispatch_epi<1, BN_SMALL>(p, (cudaStream_t)stream);
   if (p->variant == 1) return dispatch_epi<1, BN_BIG>(p, (cudaStream_t)stream);

@@ -68,6 +68,87 @@ class PeerCarry:
         return self.buf[k * self.set_bytes + off: k * self.set_bytes + off + nbytes]
 
 
+class PeerUlysses:
+    """Symmetric (peer-mapped) buffers for the attention layers' head<->sequence re-shard WITHOUT NCCL and without permute
+    copies (B == 1): the Wqkv GEMM's epilogue stores every (q|k|v, head) tile straight into the owning rank's `full`
+    buffer over NVLink (evo_gemm peer-scattered output, rotary applied on the way), the attention kernel's epilogue stores
+    every query row straight into the token-owning rank's `ctx` buffer; two flag rounds (evo_peer_publish with no payload /
+    evo_peer_wait) tell a rank when all of its inputs have landed.  `full` is double-buffered: a rank may enter the next
+    attention layer while a slower peer still reads the previous one (it cannot get two layers ahead: the layer in between
+    needs that peer's q/k/v).  Layout per rank: [full0 | full1 | ctx | q-flags | c-flags]."""
+
+    def __init__(self, world, rank, Lr, d, H, dev, group):
+        import torch.distributed._symmetric_memory as symm
+        hd = d // H
+        self.world, self.rank, self.Lr, self.d = world, rank, Lr, d
+        self.Hl, self.dl = H // world, (H // world) * hd
+        self.L = Lr * world
+        al = lambda n: (n + 255) // 256 * 256
+        self.full_bytes = al(self.L * 3 * self.dl * 2)
+        self.ctx_bytes = al(Lr * d * 2)
+        self.off_ctx = 2 * self.full_bytes
+        self.off_qflag = self.off_ctx + self.ctx_bytes
+        self.off_cflag = self.off_qflag + al(world * 4)
+        total = self.off_cflag + al(world * 4)
+        self.buf = symm.empty(total, dtype=torch.uint8, device=dev)
+        self.buf[self.off_qflag:].zero_()
+        torch.cuda.synchronize(dev)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        arr = lambda vals: (C.c_void_p * world)(*vals)
+        self.full_ptrs = [arr([x + k * self.full_bytes for x in ptrs]) for k in range(2)]
+        self.ctx_ptrs = arr([x + self.off_ctx for x in ptrs])
+        mk = lambda vals: torch.tensor(vals, dtype=torch.int64, device=dev)
+        self.dummy_dsts = mk(ptrs)                                            # payload-free publish: nothing is copied
+        self.qflag_dsts = mk([x + self.off_qflag for x in ptrs])
+        self.cflag_dsts = mk([x + self.off_cflag for x in ptrs])
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch = 0
+        self.calls = 0
+        self.key = (world, rank, Lr, d, H, str(dev))
+
+    def full(self, k):
+        return self.buf[k * self.full_bytes: k * self.full_bytes + self.L * 3 * self.dl * 2].view(torch.bfloat16)
+
+    def ctx(self):
+        return self.buf[self.off_ctx: self.off_ctx + self.Lr * self.d * 2].view(torch.bfloat16).view(self.Lr, self.d)
+
+    def signal_and_wait(self, model, lib, which, stream):
+        """All ranks: 'my stores of this phase are done' -> every peer; then wait until every rank has said so."""
+        dsts = self.qflag_dsts if which == "q" else self.cflag_dsts
+        off = self.off_qflag if which == "q" else self.off_cflag
+        w = self.world
+        model._record("comm/peer_flags", 0.0, lambda: (
+            check(lib.evo_peer_publish(ptr(self.counter), 0, ptr(self.dummy_dsts), ptr(dsts), 0, self.rank, 0, w - 1, self.epoch, ptr(self.counter), stream()), "evo_peer_publish(flags)"),
+            check(lib.evo_peer_wait(ptr(self.buf[off: off + w * 4]), 0, w - 1, self.epoch, stream()), "evo_peer_wait(flags)")))
+
+
+def _peer_attention(model, lib, pu, xn, mha, u, B, Lr, H, hd, rank, world, stream):
+    """One sequence-parallel attention layer with the re-shard fused into the GEMM / attention epilogues (PeerUlysses).
+    xn (Lr, D) = pre-norm output; returns ctx (Lr, D), this rank's tokens x all heads, ready for out_proj."""
+    d = H * hd
+    k = pu.calls % 2
+    pu.calls += 1
+    pu.epoch += 1
+    pos0 = rank * Lr
+    cos, sin = model._rope_tables(pos0 + Lr, xn.device)
+    cos_p, sin_p = cos.data_ptr() + pos0 * (hd // 2) * 2, sin.data_ptr() + pos0 * (hd // 2) * 2
+    # Wqkv: bias + rotary + scatter to the head-owning ranks, tile by tile while the GEMM runs
+    model._gemm(xn, mha.Wqkv.weight, None, Lr, 3 * d, d, EPI_BIAS_ROPE, bias=mha.Wqkv.bias, ldc=3 * pu.dl, rope=(cos_p, sin_p, Lr, 2 * d),
+                peers=(pu.full_ptrs[k], world, d, pu.dl, rank * Lr))
+    pu.signal_and_wait(model, lib, "q", stream)
+    full = pu.full(k)                                   # (L, 3, Hl, hd): my heads, the whole sequence
+    L, dl = pu.L, pu.dl
+    ap = AttnParams(out=None, B=1, Lq=L, Lk=L, H=pu.Hl, hd=hd, q_pos0=0, softmax_scale=1.0 / math.sqrt(hd))
+    ap.q, ap.q_tok_stride, ap.q_batch_stride = full.data_ptr(), 3 * dl, L * 3 * dl
+    ap.k, ap.v, ap.kv_tok_stride, ap.kv_batch_stride = full.data_ptr() + dl * 2, full.data_ptr() + 2 * dl * 2, 3 * dl, L * 3 * dl
+    ap.out_peers, ap.n_out_peers, ap.out_rows_per_peer, ap.out_row_stride, ap.out_col0 = C.cast(pu.ctx_ptrs, C.c_void_p), world, Lr, d, rank * dl
+    causal_flops = 4.0 * pu.Hl * hd * (L * (L + 1) / 2.0)
+    model._record("attn", causal_flops, lambda: check(lib.evo_attn_fwd_ws(C.byref(ap), 2, None, 0, stream()), "evo_attn_fwd(peer)"))
+    pu.signal_and_wait(model, lib, "c", stream)
+    return pu.ctx()
+
+
 def _ulysses_attention(model, lib, qkv, ctx, B, Lr, H, hd, rank, world, group, stream):
     """qkv (B*Lr, 3*H*hd) rotary-applied, sequence-sharded -> ctx (B*Lr, H*hd), sequence-sharded."""
     if H % world != 0:
@@ -132,8 +213,18 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
                 model._peer_carry_error = repr(ex)
             # the transport is a collective decision: one rank on NCCL all-gathers while the others spin on peer flags would
             # hang, so every rank learns whether ALL of them have the peer path
-            ok = torch.tensor([1 if pc is not None else 0], dtype=torch.int32, device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            pu = None
+            if pc is not None and B == 1 and H % world == 0 and model.attn_variant == 2 and model.fused_rope and model.gemm_variant in (0, 1):
+                try:
+                    pu = PeerUlysses(world, rank, Lr, d, H, dev, group)
+                except Exception as ex:  # noqa
+                    pu = None
+                    model._peer_carry_error = repr(ex)
+            okv = [1 if pc is not None else 0, 1 if pu is not None else 0]
+            ok2 = torch.tensor(okv, dtype=torch.int32, device=dev)
+            dist.all_reduce(ok2, op=dist.ReduceOp.MIN, group=group)
+            model._peer_ulysses = pu if int(ok2[1].item()) == 1 else None
+            ok = ok2[:1]
             if int(ok.item()) == 0:
                 if transport == "peer":
                     raise _lib.EvoError("peer-memory transport unavailable on at least one rank: " + str(getattr(model, "_peer_carry_error", "")))
@@ -144,6 +235,9 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
         if pc is not None:
             model._record("comm/barrier", 0.0, lambda: dist.barrier(group))          # nobody is still reading ring slots of the previous forward
     since_sync = 0
+    pu = getattr(model, "_peer_ulysses", None) if (pc is not None and transport in ("auto", "peer")) else None
+    if pu is not None and pu.key != (world, rank, Lr, d, H, str(dev)):
+        pu = None
     with torch.cuda.device(dev), torch.no_grad():
         ids_local = ids_local.contiguous()
         u = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
@@ -151,7 +245,13 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
         for i, blk in enumerate(model.blocks):
             xn = torch.empty_like(u)
             model._rmsnorm(u, blk.pre_norm.scale, xn, M)
-            if i in model._attn_idxs:
+            if i in model._attn_idxs and pu is not None:
+                mha = blk.inner_mha_cls
+                ctx = _peer_attention(model, lib, pu, xn, mha, u, B, Lr, H, hd, rank, world, stream)
+                since_sync = 0           # the flag rounds are global synchronisation points
+                u2 = torch.empty_like(u)
+                model._gemm(ctx, mha.out_proj.weight, u2, M, d, d, EPI_BIAS_RESID if mha.out_proj.bias is not None else EPI_RESID, bias=mha.out_proj.bias, resid=u)
+            elif i in model._attn_idxs:
                 mha = blk.inner_mha_cls
                 qkv = torch.empty(M, 3 * d, dtype=torch.bfloat16, device=dev)
                 pos0 = rank * Lr

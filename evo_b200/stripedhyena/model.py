@@ -299,16 +299,20 @@ class StripedHyena(nn.Module):
         e1.record()
         self._prof.append((kind, work, e0, e1))
 
-    def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None, variant=None, rope=None):
-        """rope = (cos_ptr, sin_ptr, tokens_per_sequence, rotated_columns) for EPI_BIAS_ROPE."""
+    def _gemm(self, a, w, out, M, N, K, epi, bias=None, resid=None, ldc=None, variant=None, rope=None, peers=None):
+        """rope = (cos_ptr, sin_ptr, tokens_per_sequence, rotated_columns) for EPI_BIAS_ROPE;
+        peers = (ctypes array of peer pointers, n, period, inner, row0): peer-scattered output (see evo_gemm_params), out may be None."""
         if variant is None:
             variant = self.gemm_variant_gate if epi == EPI_GELU_GATE else self.gemm_variant
-        p = GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=ldc or N,
+        p = GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr() if out is not None else None, ldc=ldc or N,
                        bias=bias.data_ptr() if bias is not None else None,
                        residual=resid.data_ptr() if resid is not None else None, ldr=ldc or N,
                        M=M, N=N, K=K, epilogue=epi, variant=variant)
         if rope is not None:
             p.rope_cos, p.rope_sin, p.rope_L, p.rope_cols = rope
+        if peers is not None:
+            arr, n, period, inner, row0 = peers
+            p.c_peers, p.n_c_peers, p.peer_period, p.peer_inner, p.peer_row0 = C.cast(arr, C.c_void_p), n, period, inner, row0
         self._record(f"gemm/{N}x{K}/e{epi}/v{variant}", 2.0 * M * N * K, lambda: check(_lib.lib().evo_gemm(C.byref(p), self._stream()), "evo_gemm"))
 
     def _gemm_smallm(self, a, w, out, M, N, K, epi, bias=None, resid=None, step=None):

@@ -79,6 +79,13 @@ typedef struct {
   const void* rope_cos; const void* rope_sin;   /* EVO_EPI_BIAS_ROPE: (positions, 64) bf16 tables (evo_rope_tables) */
   int64_t rope_L;                /* tokens per sequence: row m uses table row m % rope_L */
   int64_t rope_cols;             /* columns [0, rope_cols) are rotated (2*H*128 for a qkv projection), the rest only get the bias */
+  /* Peer-scattered output (n_c_peers > 0): the epilogue stores straight into up to 8 peer-mapped buffers over NVLink, i.e.
+   * the Ulysses head<->sequence all-to-all of a sequence-parallel attention layer fused into the Wqkv GEMM (no NCCL, no
+   * permute): column n of row m goes to c_peers[(n % peer_period) / peer_inner], element
+   * (peer_row0 + m) * ldc + (n / peer_period) * peer_inner + n % peer_inner.  For qkv (3, H, 128) and P ranks:
+   * peer_period = H*128, peer_inner = H/P*128, ldc = 3*peer_inner, peer_row0 = rank * rows.  C is ignored. */
+  void* const* c_peers;          /* HOST array of n_c_peers device pointers */
+  int n_c_peers; int64_t peer_period, peer_inner, peer_row0;
 } evo_gemm_params;
 int evo_gemm(const evo_gemm_params* p, void* stream);
 /* Decode-step linear layer (M <= 64 rows): the same C = epilogue(A . W^T) with the same rounding points, as a
@@ -177,6 +184,11 @@ typedef struct {
   int B; int64_t Lq, Lk; int H; int hd;
   int64_t q_pos0;
   float softmax_scale;
+  /* Peer-scattered output (n_out_peers > 0; variant 2, B == 1): query row i is stored into
+   * out_peers[i / out_rows_per_peer] at element (i % out_rows_per_peer) * out_row_stride + out_col0 + h*128 -- the return
+   * all-to-all of a sequence-parallel attention layer fused into the attention epilogue.  `out` is ignored. */
+  void* const* out_peers;        /* HOST array of device pointers */
+  int n_out_peers; int64_t out_rows_per_peer, out_row_stride, out_col0;
 } evo_attn_params;
 /* variant 0: V is transposed into the workspace first and consumed as a K-major operand;
  * variant 1: V is consumed in place as an MN-major operand (no workspace);

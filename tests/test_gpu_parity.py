@@ -141,6 +141,53 @@ def test_gemm_rotary_epilogue_equals_projection_then_rotary(variant, B, L, H, of
     assert _lib.lib().evo_gemm(C.byref(bad), stream()) != 0
 
 
+def test_peer_scattered_outputs_of_gemm_and_attention_on_one_gpu():
+    """The Ulysses re-shard fused into the epilogues (evo_gemm c_peers / evo_attn out_peers), exercised with the 'peers' being
+    four buffers on THIS GPU: the scatter must equal the permute the NCCL path does (parallel._ulysses_attention)."""
+    P, Lr, H, K = 4, 256, 8, 256
+    d, Hl = H * 128, H // P
+    dl = Hl * 128
+    L = P * Lr
+    torch.manual_seed(12)
+    w = (torch.randn(3 * d, K, device=DEV) / 16).bfloat16()
+    bias = torch.randn(3 * d, device=DEV).bfloat16()
+    cos, sin = O.rotary_tables(L, 128, dtype=torch.bfloat16)
+    cd, sd_ = cos.to(DEV), sin.to(DEV)
+    full = [torch.full((L, 3, Hl, 128), float("nan"), dtype=torch.bfloat16, device=DEV) for _ in range(P)]      # one per "rank"
+    arr = (C.c_void_p * P)(*[f.data_ptr() for f in full])
+    want_qkv = []
+    for r in range(P):                                                       # every "rank" projects its own Lr tokens
+        a = (torch.randn(Lr, K, device=DEV) * 0.7).bfloat16()
+        ref = G._gemm(a, w, Lr, 3 * d, K, _lib.EPI_BIAS, 0, bias=bias)
+        _lib.check(_lib.lib().evo_rotary_qk(_lib.ptr(ref), C.c_void_p(cd.data_ptr() + r * Lr * 128), C.c_void_p(sd_.data_ptr() + r * Lr * 128), 1, Lr, H, 128, stream()))
+        want_qkv.append(ref.view(Lr, 3, P, Hl, 128))
+        p = _lib.GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=None, ldc=3 * dl, bias=bias.data_ptr(), residual=None, ldr=3 * dl, M=Lr, N=3 * d, K=K,
+                            epilogue=_lib.EPI_BIAS_ROPE, variant=0, rope_cos=cd.data_ptr() + r * Lr * 128, rope_sin=sd_.data_ptr() + r * Lr * 128, rope_L=Lr, rope_cols=2 * d,
+                            c_peers=C.cast(arr, C.c_void_p), n_c_peers=P, peer_period=d, peer_inner=dl, peer_row0=r * Lr)
+        _lib.check(_lib.lib().evo_gemm(C.byref(p), stream()), "evo_gemm(peers)")
+    torch.cuda.synchronize()
+    whole = torch.cat(want_qkv, 0)                                           # (L, 3, P, Hl, 128)
+    for pr in range(P):
+        assert not torch.isnan(full[pr].float()).any()
+        assert (full[pr] == whole[:, :, pr]).float().mean().item() > 0.9999   # fma contraction in the fused rotary may flip a last bit
+    # attention of "rank" 1's heads over the whole sequence, rows scattered to the four token owners' ctx buffers
+    ctxs = [torch.full((Lr, d), float("nan"), dtype=torch.bfloat16, device=DEV) for _ in range(P)]
+    carr = (C.c_void_p * P)(*[c.data_ptr() for c in ctxs])
+    me = 1
+    f = full[me]
+    plain = G._attn(f.view(1, L, 3, Hl, 128), 1, L, Hl, 2)                      # (1, L, dl)
+    ap = _lib.AttnParams(out=None, B=1, Lq=L, Lk=L, H=Hl, hd=128, q_pos0=0, softmax_scale=1 / math.sqrt(128))
+    ap.q, ap.q_tok_stride, ap.q_batch_stride = f.data_ptr(), 3 * dl, L * 3 * dl
+    ap.k, ap.v, ap.kv_tok_stride, ap.kv_batch_stride = f.data_ptr() + dl * 2, f.data_ptr() + 2 * dl * 2, 3 * dl, L * 3 * dl
+    ap.out_peers, ap.n_out_peers, ap.out_rows_per_peer, ap.out_row_stride, ap.out_col0 = C.cast(carr, C.c_void_p), P, Lr, d, me * dl
+    _lib.check(_lib.lib().evo_attn_fwd_ws(C.byref(ap), 2, None, 0, stream()), "evo_attn_fwd(peers)")
+    torch.cuda.synchronize()
+    for r in range(P):
+        assert torch.equal(ctxs[r][:, me * dl:(me + 1) * dl], plain[0, r * Lr:(r + 1) * Lr])
+        assert torch.isnan(ctxs[r][:, :me * dl].float()).all() and torch.isnan(ctxs[r][:, (me + 1) * dl:].float()).all()     # other ranks' columns untouched
+    assert _lib.lib().evo_attn_fwd_ws(C.byref(ap), 1, None, 0, stream()) != 0                                          # variant 1 refuses
+
+
 def test_kv_append_and_logprobs():
     lib = _lib.lib()
     qkv = torch.randn(2, 5, 3, 2, 128).bfloat16()
