@@ -20,12 +20,17 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.distributed as dist
 
 from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_RESID, EPI_BIAS_ROPE, EPI_NONE, EPI_RESID, AttnParams, HyenaParams, check, ptr
+
+
+# attention re-shard through our own NVLink peer stores (PeerUlysses) instead of NCCL all-to-alls; "0" = NCCL Ulysses
+PEER_ULYSSES = os.environ.get("EVO_B200_PEER_ULYSSES", "0") != "0"
 
 
 def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
@@ -214,7 +219,7 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
             # the transport is a collective decision: one rank on NCCL all-gathers while the others spin on peer flags would
             # hang, so every rank learns whether ALL of them have the peer path
             pu = None
-            if pc is not None and B == 1 and H % world == 0 and model.attn_variant == 2 and model.fused_rope and model.gemm_variant in (0, 1):
+            if PEER_ULYSSES and pc is not None and B == 1 and H % world == 0 and model.attn_variant == 2 and model.fused_rope and model.gemm_variant in (0, 1):
                 try:
                     pu = PeerUlysses(world, rank, Lr, d, H, dev, group)
                 except Exception as ex:  # noqa
