@@ -305,6 +305,8 @@ def sp131k_record(model8k, world, rank, dev, steps, warmup, peaks):
     if world > 1:
         tr = getattr(model, "_peer_carry", None)
         rec["hyena_carry_transport"] = "nvlink peer stores + flags (own kernels)" if tr not in (None, False) else "nccl all-gather"
+        rec["attention_reshard"] = ("nvlink peer stores fused into the Wqkv GEMM / attention epilogues + flag rounds (own kernels)"
+                                    if getattr(model, "_peer_ulysses", None) is not None else "nccl all_to_all (Ulysses) + permute copies")
     # rank 0's instrumented step: kernels and communication, each as ms per step; what no event covered is host-side gaps
     comm = {k.split("/", 1)[1]: v[1] for k, v in by.items() if k.startswith("comm/")}
     kern = {k: v[1] for k, v in by.items() if not k.startswith("comm/")}
