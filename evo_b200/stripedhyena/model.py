@@ -210,8 +210,12 @@ class StripedHyena(nn.Module):
         self.decode_streamk = os.environ.get("EVO_B200_DECODE_STREAMK", "1") != "0"
         # programmatic dependent launch inside a decode step (evo_set_pdl): 0 off, 1 every kernel, 2 weight-streaming GEMMs only
         self.decode_pdl = int(os.environ.get("EVO_B200_DECODE_PDL", "2"))
-        # the Hyena decode step inside the in-projection GEMM's epilogue (EVO_EPI_HYENA_STEP); "0" = separate evo_hyena_step launch
-        self.decode_fused_step = os.environ.get("EVO_B200_DECODE_FUSED_STEP", "1") != "0"
+        # the Hyena decode step inside the in-projection GEMM's epilogue (EVO_EPI_HYENA_STEP).  Bit-identical to the separate
+        # evo_hyena_step launch but SLOWER on B200 (5.12 vs 4.30 ms/step at batch 16, profiles/r02_decode_fused_step_call8.txt): the
+        # step of a tile runs on the 128 epilogue threads of its last contributor -- 16 batch rows x 8 states of dependent
+        # load -> update -> store per thread in the GEMM's serial tail -- where the stand-alone kernel spreads the same 8 MB of state
+        # traffic over 524 288 threads.  Off by default; kept as a tested option.
+        self.decode_fused_step = os.environ.get("EVO_B200_DECODE_FUSED_STEP", "0") != "0"
         self._smallm_ws = None
         self._tiled = None   # tile-major weight copies for the weight-streaming decode GEMMs
         self._decode = None  # cached CUDA graph of one decode step (see _decode_forward)
