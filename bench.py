@@ -27,6 +27,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: NCCL's banner ("NCCL version ..." when the pod sets NCCL_DEBUG=VERSION) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 WORKLOADS = {
     "8k": dict(model="evo-1-8k-base", batch=8, nt=8192, desc="evo-1-8k-base 7B scoring forward, batch 8 x 8192 nt (+BOS), bf16"),

@@ -64,6 +64,7 @@ struct GemmArgs {
   long long rope_L, rope_cols;                  //   rows repeat with period rope_L (tokens per sequence); columns < rope_cols (q and k) are rotated
   const long long* targets;   // EPI_LSE only: (M) target token per row (-1: none)
   float4* part;               // EPI_LSE only: (M, n_blocks) per-row partial statistics {max, sum e^(x-max), sum e^(x-max) x, target logit}
+  int l2_hints;          // TMA loads carry L2 eviction priorities (resident slab evict_last, streaming operand evict_first)
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
 
@@ -234,6 +235,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t full_leader_mask = 0xFEFFFFFFu;   // shared::cluster address of the pair leader's copy
+      // the slab the rasterisation keeps resident is evict_last, the operand streaming past it evict_first (g.l2_hints; 0 = plain loads)
+      const uint64_t pol_a = g.l2_hints ? (g.raster_n ? l2_policy_evict_first() : l2_policy_evict_last()) : 0;
+      const uint64_t pol_b = g.l2_hints ? (g.raster_n ? l2_policy_evict_last() : l2_policy_evict_first()) : 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_step) {
         int m_blk, n_blk; tile_coords(tile, g, m_blk, n_blk);
         const int a_row = (m_blk * CG + (int)cta_rank) * BM;
@@ -243,6 +247,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (CG == 1) {
             mbar_arrive_expect_tx(&full[stage], STAGE_TX);
             for (int u = 0; u < KSUB; ++u) {
+              if (!SMALL && g.l2_hints) {
+                tma_load_2d_hint(smA + (stage * KSUB + u) * A_STRIDE, &tmA, &full[stage], (kb * KSUB + u) * BK, a_row, pol_a);
+                tma_load_2d_hint(smB + (stage * KSUB + u) * C_::B_BYTES, &tmB, &full[stage], (kb * KSUB + u) * BK, b_row, pol_b);
+                continue;
+              }
               tma_load_2d(smA + (stage * KSUB + u) * A_STRIDE, &tmA, &full[stage], (kb * KSUB + u) * BK, a_row);
               if (SMALL && g.b_tiled) tma_load_4d(smB + (stage * KSUB + u) * C_::B_BYTES, &tmB, &full[stage], 0, 0, kb * KSUB + u, n_blk);
               else tma_load_2d(smB + (stage * KSUB + u) * C_::B_BYTES, &tmB, &full[stage], (kb * KSUB + u) * BK, b_row);
@@ -252,8 +261,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // 512-cycle k-block budget; the peer's bytes are already counted in the leader's expect_tx
             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C_::STAGE_BYTES);
             const uint32_t bar = smem_u32(&full[stage]) & full_leader_mask;
-            tma_load_2d_2sm(smA + stage * C_::A_BYTES, &tmA, bar, kb * BK, a_row);
-            tma_load_2d_2sm(smB + stage * C_::B_BYTES, &tmB, bar, kb * BK, b_row);
+            if (g.l2_hints) {
+              tma_load_2d_2sm_hint(smA + stage * C_::A_BYTES, &tmA, bar, kb * BK, a_row, pol_a);
+              tma_load_2d_2sm_hint(smB + stage * C_::B_BYTES, &tmB, bar, kb * BK, b_row, pol_b);
+            } else {
+              tma_load_2d_2sm(smA + stage * C_::A_BYTES, &tmA, bar, kb * BK, a_row);
+              tma_load_2d_2sm(smB + stage * C_::B_BYTES, &tmB, bar, kb * BK, b_row);
+            }
           }
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
@@ -406,6 +420,8 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
     const double traffic_n = w_tot + a_tot * std::ceil((double)g.n_blocks / gn);
     g.raster_n = traffic_n < traffic_m;
     g.group_m = g.raster_n ? gn : gm;
+    static const char* env_h = getenv("EVO_B200_GEMM_L2_HINTS");   // "0": plain TMA loads (A/B experiments)
+    g.l2_hints = (BN == BN_BIG && !(env_h && atoi(env_h) == 0)) ? 1 : 0;
     static const char* env_g = getenv("EVO_B200_GEMM_GROUP");      // experiments only
     static const char* env_r = getenv("EVO_B200_GEMM_RASTER_N");
     if (env_r) g.raster_n = atoi(env_r);
