@@ -110,10 +110,9 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-// L2 eviction-priority policies for TMA loads: the operand slab a rasterisation keeps resident is loaded evict_last, the
-// operand that streams past it evict_first, so the stream cannot push the slab out of L2 (plain LRU lets 0.5 GB of A
-// flush a 40 MB W slab between two waves: ncu showed 3-6x the algorithmic DRAM reads).
+// L2 eviction-priority policies for TMA loads (GEMM rasterisation experiments: see gemm_tcgen05.cu's producer).
 __device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t policy) {
   asm volatile(

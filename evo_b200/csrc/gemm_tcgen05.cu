@@ -235,9 +235,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t full_leader_mask = 0xFEFFFFFFu;   // shared::cluster address of the pair leader's copy
-      // the slab the rasterisation keeps resident is evict_last, the operand streaming past it evict_first (g.l2_hints; 0 = plain loads)
-      const uint64_t pol_a = g.l2_hints ? (g.raster_n ? l2_policy_evict_first() : l2_policy_evict_last()) : 0;
-      const uint64_t pol_b = g.l2_hints ? (g.raster_n ? l2_policy_evict_last() : l2_policy_evict_first()) : 0;
+      // L2 eviction priorities (experiment, EVO_B200_GEMM_L2_HINTS; default 0 = plain loads).  1: resident slab evict_last, streaming
+      // operand evict_first -- measured WORSE on B200 (profiles/r02_gemm_l2_hints_call11.txt: DRAM bytes 5.5 -> 10.6 GB for the
+      // projection, 89.2 -> 84.0 k nt/s): an evict_first tile is dropped before the other CTAs of the wave have fetched it.
+      // 2: only the slab is marked (evict_last), the stream keeps the default policy.
+      const uint64_t keep = l2_policy_evict_last(), first = g.l2_hints == 1 ? l2_policy_evict_first() : l2_policy_evict_normal();
+      const uint64_t pol_a = g.raster_n ? first : keep;
+      const uint64_t pol_b = g.raster_n ? keep : first;
       for (int tile = tile0; tile < n_tiles; tile += tile_step) {
         int m_blk, n_blk; tile_coords(tile, g, m_blk, n_blk);
         const int a_row = (m_blk * CG + (int)cta_rank) * BM;
@@ -420,8 +424,8 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
     const double traffic_n = w_tot + a_tot * std::ceil((double)g.n_blocks / gn);
     g.raster_n = traffic_n < traffic_m;
     g.group_m = g.raster_n ? gn : gm;
-    static const char* env_h = getenv("EVO_B200_GEMM_L2_HINTS");   // "0": plain TMA loads (A/B experiments)
-    g.l2_hints = (BN == BN_BIG && !(env_h && atoi(env_h) == 0)) ? 1 : 0;
+    static const char* env_h = getenv("EVO_B200_GEMM_L2_HINTS");   // experiments only: 0 (default) plain TMA loads, 1 / 2 see the producer
+    g.l2_hints = (BN == BN_BIG && env_h) ? atoi(env_h) : 0;
     static const char* env_g = getenv("EVO_B200_GEMM_GROUP");      // experiments only
     static const char* env_r = getenv("EVO_B200_GEMM_RASTER_N");
     if (env_r) g.raster_n = atoi(env_r);
