@@ -333,6 +333,27 @@ def sp131k_record(model8k, world, rank, dev, steps, warmup, peaks):
     return rec
 
 
+def sweep_record(model8k, dev, steps=3, warmup=1):
+    """BASELINE.json configs[4] at one GPU: the same 65 536-token budget as 1k and 32k sequences (8k is the headline `value`,
+    131k the `sp131k` record).  nt/s with ids resident in HBM, CUDA events around `steps` forwards."""
+    import torch
+    from evo_b200 import CharLevelTokenizer, prepare_batch
+    tok = CharLevelTokenizer(512)
+    out = {}
+    for key in ("1k", "32k"):
+        wl = WORKLOADS[key]
+        m = model8k if wl["model"] == "evo-1-8k-base" else variant_of(model8k, wl["model"])
+        ids, _ = prepare_batch(synthetic_seqs(wl["batch"], wl["nt"], seed=7), tok, prepend_bos=True, device=dev)
+        fwd = lambda: m(ids)
+        for _ in range(warmup):
+            fwd()
+        ms, _ = time_steps(fwd, steps, 1, dev)
+        out[key] = {"workload": wl["desc"], "value": wl["batch"] * wl["nt"] * steps / (ms / 1e3), "unit": "nt/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup}
+        del ids
+        torch.cuda.empty_cache()
+    return out
+
+
 def bench_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -405,6 +426,11 @@ def bench_ours(args, wl):
                 sub["gen"] = generate_record(model, dev, peaks)
             except Exception as ex:  # noqa
                 sub["gen"] = {"error": repr(ex)[:300]}
+        if world == 1:
+            try:
+                sub["sweep"] = sweep_record(model, dev)
+            except Exception as ex:  # noqa
+                sub["sweep"] = {"error": repr(ex)[:300]}
 
     if rank == 0:
         roof = rooflines(by, prof_ms, args.workload, peaks)
