@@ -338,10 +338,10 @@ int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], con
 
 }  // namespace
 
-int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const evo_attn_params* p, cudaStream_t st);   // attention_pp.cu
+int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const evo_attn_params* p, cudaStream_t st, int npoly);   // attention_pp.cu
 
 extern "C" size_t evo_attn_fwd_workspace(const evo_attn_params* p, int variant) {
-  if (variant == 1 || variant == 2) return 0;
+  if (variant == 1 || variant == 2 || variant == 3) return 0;
   long long lpad = (p->Lk + 7) / 8 * 8;
   return (size_t)p->B * p->H * HD * lpad * 2;
 }
@@ -352,7 +352,7 @@ extern "C" int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* work
               "evo_attn_fwd: strides must be multiples of 8 elements");
   EVO_REQUIRE(p->q_pos0 + p->Lq <= p->Lk, "evo_attn_fwd: queries extend past the keys (q_pos0 %lld + Lq %lld > Lk %lld)",
               (long long)p->q_pos0, (long long)p->Lq, (long long)p->Lk);
-  EVO_REQUIRE(p->n_out_peers == 0 || variant == 2, "evo_attn_fwd: peer-scattered output is implemented by variant 2 only");
+  EVO_REQUIRE(p->n_out_peers == 0 || variant == 2 || variant == 3, "evo_attn_fwd: peer-scattered output is implemented by variants 2 and 3 only");
   if (p->Lq == 0 || p->B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmQ, tmK, tmV;
@@ -368,9 +368,9 @@ extern "C" int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* work
     uint64_t str[3] = {(uint64_t)HD * 2, (uint64_t)p->kv_tok_stride * 2, (uint64_t)p->kv_batch_stride * 2};
     uint32_t box[4] = {64, 1, BKV, 1};
     if ((rc = make_tmap_4d(&tmK, p->k, dims, str, box))) return rc;
-    if (variant == 1 || variant == 2) { if ((rc = make_tmap_4d(&tmV, p->v, dims, str, box))) return rc; }
+    if (variant == 1 || variant == 2 || variant == 3) { if ((rc = make_tmap_4d(&tmV, p->v, dims, str, box))) return rc; }
   }
-  if (variant == 2) return evo_attn_pp_launch(tmQ, tmK, tmV, p, st);
+  if (variant == 2 || variant == 3) return evo_attn_pp_launch(tmQ, tmK, tmV, p, st, variant == 3 ? 3 : 0);
   if (variant != 1) {
     long long lpad = (p->Lk + 7) / 8 * 8;
     size_t need = evo_attn_fwd_workspace(p, variant);

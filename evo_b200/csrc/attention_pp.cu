@@ -62,6 +62,25 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
         "r"(taddr) : "memory");
 }
 
+// 2^x for a pair of scores on the FMA pipe (variant 3): round-to-nearest range reduction with the 1.5*2^23 trick, a cubic
+// in f = x - round(x) in [-0.5, 0.5] (near-minimax for the relative error: 7.5e-5, a fiftieth of the bf16 rounding P gets next),
+// and the exponent added as an integer.  x is clamped at -126 (masked scores are -inf: they become 2^-126, which rounds to 0
+// against any row sum).  7 packed fma-pipe instructions + 4 ALU per PAIR, against 2 MUFU.EX2 at 8 issue cycles each.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 xi = __fadd2_rn(t, nmagic);
+  const float2 f = __ffma2_rn(xi, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(make_float2(0.0551716648f, 0.0551716648f), f, make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)), __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
+// NPOLY: of every 8 score pairs, how many take exp2_poly2 instead of MUFU.EX2 (0 = variant 2; 3 = variant 3: MUFU and the FMA
+// pipe finish a tile's exponentials at about the same time)
+template <int NPOLY>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const Args a) {
@@ -222,16 +241,38 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         // ---- P = exp2(s*scale - m_ref) as bf16, written over the S columns (all of S is in registers by now)
         float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+        if constexpr (NPOLY == 0) {
 #pragma unroll
-        for (int c = 0; c < BKV; c += 32) {
-          uint32_t w[16];
+          for (int c = 0; c < BKV; c += 32) {
+            uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2(fmaf(sc[c + 2 * i], a.scale_log2, -m_ref)), p1 = ex2(fmaf(sc[c + 2 * i + 1], a.scale_log2, -m_ref));
-            if (i & 1) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
-            w[i] = pack_bf16(p0, p1);
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2(fmaf(sc[c + 2 * i], a.scale_log2, -m_ref)), p1 = ex2(fmaf(sc[c + 2 * i + 1], a.scale_log2, -m_ref));
+              if (i & 1) { ls2 += p0; ls3 += p1; } else { ls0 += p0; ls1 += p1; }
+              w[i] = pack_bf16(p0, p1);
+            }
+            tmem_st_32x32_x16(s_addr + c / 2, w);
           }
-          tmem_st_32x32_x16(s_addr + c / 2, w);
+        } else {
+          // packed arithmetic (one FFMA2 scales two scores, one FADD2 sums two probabilities) and NPOLY of every 8 pairs
+          // exponentiated on the FMA pipe, interleaved with the MUFU pairs so that both pipes stay busy inside one warp
+          const float2 scale2 = make_float2(a.scale_log2, a.scale_log2), nm2 = make_float2(-m_ref, -m_ref);
+          float2 la = make_float2(0.f, 0.f), lb = la;
+#pragma unroll
+          for (int c = 0; c < BKV; c += 32) {
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 x = __ffma2_rn(make_float2(sc[c + 2 * i], sc[c + 2 * i + 1]), scale2, nm2);
+              float2 p;
+              if ((i & 7) * NPOLY % 8 < NPOLY) p = exp2_poly2(x);      // NPOLY pairs of 8, spread evenly
+              else p = make_float2(ex2(x.x), ex2(x.y));
+              if (i & 1) lb = __fadd2_rn(lb, p); else la = __fadd2_rn(la, p);
+              w[i] = pack_bf16(p.x, p.y);
+            }
+            tmem_st_32x32_x16(s_addr + c / 2, w);
+          }
+          ls0 = la.x + lb.x; ls1 = la.y + lb.y;
         }
         const float ls0_ = ls0 + ls2, ls1_ = ls1 + ls3;
         ls0 = ls0_; ls1 = ls1_;
@@ -278,7 +319,7 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }  // namespace evo_attn_pp
 
 // called from evo_attn_fwd_ws (attention.cu) for variant 2
-int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const evo_attn_params* p, cudaStream_t st) {
+int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const evo_attn_params* p, cudaStream_t st, int npoly) {
   using namespace evo_attn_pp;
   Args a;
   a.out = (bf16*)p->out; a.B = p->B; a.H = p->H; a.Lq = p->Lq; a.Lk = p->Lk; a.q_pos0 = p->q_pos0;
@@ -291,9 +332,14 @@ int evo_attn_pp_launch(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
                 p->out_rows_per_peer * p->n_out_peers >= p->Lq && p->out_row_stride % 8 == 0 && p->out_col0 % 8 == 0,
                 "evo_attn_fwd: peer-scattered output needs B == 1, 1..8 peers covering Lq rows, 16-byte aligned strides");
   }
-  static unsigned long long done = 0;
-  { int rc_ = ensure_dyn_smem(attn_pp_kernel, SMEM, done); if (rc_) return rc_; }
+  static unsigned long long done0 = 0, done3 = 0;
   dim3 grid((unsigned)((a.n_qblk + 1) / 2), p->H, p->B);
-  attn_pp_kernel<<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, a);
+  if (npoly == 0) {
+    { int rc_ = ensure_dyn_smem(attn_pp_kernel<0>, SMEM, done0); if (rc_) return rc_; }
+    attn_pp_kernel<0><<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, a);
+  } else {
+    { int rc_ = ensure_dyn_smem(attn_pp_kernel<3>, SMEM, done3); if (rc_) return rc_; }
+    attn_pp_kernel<3><<<grid, THREADS, SMEM, st>>>(tmQ, tmK, tmV, a);
+  }
   return check_launch("evo_attn_fwd(pp)");
 }

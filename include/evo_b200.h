@@ -192,7 +192,8 @@ typedef struct {
 } evo_attn_params;
 /* variant 0: V is transposed into the workspace first and consumed as a K-major operand;
  * variant 1: V is consumed in place as an MN-major operand (no workspace);
- * variant 2: ping-pong kernel: two query tiles per CTA, P kept in TMEM (A operand from TMEM), V in place. */
+ * variant 2: ping-pong kernel: two query tiles per CTA, P kept in TMEM (A operand from TMEM), V in place;
+ * variant 3: variant 2 with packed softmax arithmetic and 3 of every 8 exponentials evaluated on the FMA pipe (cubic). */
 size_t evo_attn_fwd_workspace(const evo_attn_params* p, int variant);
 int evo_attn_fwd_ws(const evo_attn_params* p, int variant, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -141,15 +141,17 @@ def test_hyena_131072_tokens_poles_near_the_unit_circle(nseg):
 
 
 # ------------------------------------------------------------------ attention, shipped variant, full head count / long rope
-def test_attention_variant2_32_heads_8193_vs_oracle():
-    """The default attention kernel at H = 32, L = 8193: every head against the independent CUDA-core comparator, four
-    heads (first, two interior, last) against the CPU oracle in bf16-faithful and fp64 arithmetic."""
+@pytest.mark.parametrize("variant", [2, 3])
+def test_attention_variant2_32_heads_8193_vs_oracle(variant):
+    """The ping-pong attention kernel (variant 2; 3 = with part of the exponentials on the FMA pipe) at H = 32, L = 8193: every
+    head against the independent CUDA-core comparator, four heads (first, two interior, last) against the CPU oracle in
+    bf16-faithful and fp64 arithmetic."""
     from tests import support as TS
     B, L, H = 1, 8193, 32
     torch.manual_seed(8)
     qkv = torch.randn(B, L, 3, H, 128).bfloat16()
-    out = G._attn(qkv.to(DEV), B, L, H, 2)
-    comp = G._attn(qkv.to(DEV), B, L, H, 2, simple=True)
+    out = G._attn(qkv.to(DEV), B, L, H, variant)
+    comp = G._attn(qkv.to(DEV), B, L, H, variant, simple=True)
     assert not torch.isnan(out.float()).any()
     assert maxerr(out, comp) <= 4 * BF16_EPS * max(1.0, comp.float().abs().max().item())
     assert meanerr(out, comp) < 2e-4

@@ -454,7 +454,7 @@ def test_gemm_full_size_against_cublaslt():
 
 
 # ------------------------------------------------------------------ attention
-@pytest.mark.parametrize("variant", [1, 0, 2])
+@pytest.mark.parametrize("variant", [1, 0, 2, 3])
 @pytest.mark.parametrize("B,L", [(1, 1), (2, 37), (1, 128), (2, 129), (1, 256), (1, 300), (2, 1000), (1, 2500)])
 def test_attention_vs_oracle(variant, B, L):
     H = 2
@@ -470,7 +470,7 @@ def test_attention_vs_oracle(variant, B, L):
     assert maxerr(simple, ref) <= 4 * BF16_EPS * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("variant", [1, 0, 2])
+@pytest.mark.parametrize("variant", [1, 0, 2, 3])
 def test_attention_kv_cache_form(variant):
     B, H, Lc = 2, 2, 512
     torch.manual_seed(5)
