@@ -29,8 +29,10 @@ from . import _lib
 from ._lib import EPI_BIAS, EPI_BIAS_RESID, EPI_BIAS_ROPE, EPI_NONE, EPI_RESID, AttnParams, HyenaParams, check, ptr
 
 
-# attention re-shard through our own NVLink peer stores (PeerUlysses) instead of NCCL all-to-alls; "0" = NCCL Ulysses
-PEER_ULYSSES = os.environ.get("EVO_B200_PEER_ULYSSES", "0") != "0"
+# attention re-shard through our own NVLink peer stores (PeerUlysses) instead of NCCL all-to-alls; "0" = NCCL Ulysses.
+# Validated on 2 and 8 GPUs (profiles/r02_seqpar_check_{2gpu_peer_ulysses_call10,8gpu_call13}.json: identical to the NCCL path on
+# every rank; r02_sp{2,8}_peer_ulysses_ab_*.txt: 0.3-1.4 % faster on one box).
+PEER_ULYSSES = os.environ.get("EVO_B200_PEER_ULYSSES", "1") != "0"
 
 
 def _all_gather(t: torch.Tensor, world: int, group=None) -> torch.Tensor:
