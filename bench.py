@@ -271,8 +271,9 @@ def variant_of(model, model_name):
     m = copy.copy(model)
     m.config = dotdict(get_config(model_name))
     m._rope, m._decode, m._prof = None, None, None
-    if hasattr(m, "_peer_carry"):
-        del m._peer_carry
+    for attr in ("_peer_carry", "_peer_ulysses"):          # symmetric-memory state belongs to the (shape, config) it was built for
+        if hasattr(m, attr):
+            delattr(m, attr)
     return m
 
 
