@@ -2,6 +2,7 @@
 the StripedHyena parameter tree / strict loading, and the generation loop's state protocol
 (driven with a CPU stand-in model)."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -423,3 +424,25 @@ def test_frontend_fasta_reader_and_length_buckets(tmp_path):
         assert 1.0 - sum(len(seqs[i]) for i in b) / (width * len(b)) <= 0.25 + 1e-9
     with pytest.raises(ValueError):
         length_buckets(seqs, mode="nope")
+
+
+@pytest.mark.timeout(240)
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours): exactly one JSON line on stdout carrying the
+    contract's keys, a cpu_baseline that describes the run, and an e2e that repeats the line's own value with no copies."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=220, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "nt/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and "sample" in cb and abs(cb["value"] - d["value"]) < 1e-6
+    assert d["e2e"] == {"value": d["value"], "unit": "nt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
