@@ -152,11 +152,12 @@ def bench_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, m, run = cpu_baseline(wl["model"], target_seconds=8.0)
+    steps = args.steps if args.steps is not None else 3
+    # one step = one bounded sample; the sample shrinks with the step count so that the whole arm stays near two minutes
+    base, m, run = cpu_baseline(wl["model"], target_seconds=max(2.0, min(8.0, 100.0 / max(steps, 1))))
     L = int(base["sample"].split(" x ")[1].split(" nt")[0])
     for _ in range(args.warmup if args.warmup is not None else 1):
         run(min(L, 128))
-    steps = args.steps if args.steps is not None else 3
     t0 = time.perf_counter()
     for _ in range(steps):
         run(L)
