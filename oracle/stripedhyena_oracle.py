@@ -7,9 +7,10 @@ only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 PARITY UNPINNED (stated as the task requires): the arithmetic of the reference
 path lives in the third-party package ``stripedhyena==0.2.2`` (pinned at
 /root/reference/requirements.txt:1 and environment.yml:10), which is neither
-vendored in /root/reference nor installed in the build container, and the
-reference repository has no tests, golden vectors or fixtures for this path
-(SURVEY.md section 4, section 8c).  This file therefore RESTATES the published
+vendored in /root/reference nor installed in the build container -- nor obtainable on the
+GPU box (round 2: no package index, no wheel in /opt/wheelhouse, no HF cache; log in
+profiles/r02_pin_attempt_call1.log) -- and the reference repository has no tests, golden
+vectors or fixtures for this path.  This file therefore RESTATES the published
 algorithm of stripedhyena 0.2.2 (model.py / engine.py / layers.py / cache.py /
 sample.py / positional_embeddings.py of github.com/togethercomputer/stripedhyena
 at the 0.2.x tag) in plain PyTorch, anchored on the reference's call sites:
