@@ -88,3 +88,37 @@ def test_streaming_ingest_to_the_gpu_and_bucketed_scoring(tmp_path):
     single = [float(evo_b200.score_sequences([s], a, tok, device=DEV)[0]) for s in seqs]
     assert np.allclose(many, single, atol=2e-2)                   # padding changes nothing causal; batch shapes change bf16 GEMM tiling only
     assert len(many) == len(seqs)
+
+
+def test_public_scoring_entry_points_take_the_device_front_end_and_the_fused_head(monkeypatch):
+    """Routing, not numbers: score_sequences / positional_entropies must tokenise on the GPU (frontend.device_batch ->
+    evo_tokenize_pad) and read their statistics from the fused head (model.score_tokens -> evo_unembed_score), never from
+    materialised logits; the library's launch counter sees exactly the extra launches of that route."""
+    import evo_b200
+    from evo_b200 import frontend
+    from evo_b200.stripedhyena import StripedHyena, dotdict
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    m = StripedHyena(dotdict(cfg))
+    m.load_state_dict(O.random_state_dict(cfg, seed=2), strict=True)
+    m.to_bfloat16_except_poles_residues()
+    m = m.to(DEV)
+    calls = {"batch": 0, "score": 0, "forward": 0}
+    real_batch, real_score, real_forward = frontend.device_batch, m.score_tokens, m.forward
+    monkeypatch.setattr(frontend, "device_batch", lambda *a, **k: (calls.__setitem__("batch", calls["batch"] + 1), real_batch(*a, **k))[1])
+    m.score_tokens = lambda *a, **k: (calls.__setitem__("score", calls["score"] + 1), real_score(*a, **k))[1]
+    m.forward = lambda *a, **k: (calls.__setitem__("forward", calls["forward"] + 1), real_forward(*a, **k))[1]
+    tok = CharLevelTokenizer(512)
+    lib = _lib.lib()
+    lib.evo_reset_launch_count()
+    s = evo_b200.score_sequences(["ACGTACGTAC", "TTGACA"], m, tok, device=DEV)
+    n_score = lib.evo_launch_count()
+    e = evo_b200.positional_entropies(["ACGTACGTAC", "TTGACA"], m, tok, device=DEV)
+    assert calls == {"batch": 2, "score": 2, "forward": 0}
+    assert len(s) == 2 and [len(x) for x in e] == [10, 6]
+    # tokenise + embed + 2 blocks + final norm + fused head (GEMM + finish): the plain forward would end in one GEMM and a logprobs kernel
+    lib.evo_reset_launch_count()
+    ids, _ = prepare_batch(["ACGTACGTAC", "TTGACA"], tok, device=DEV)
+    n_tok = lib.evo_launch_count()
+    real_forward(ids)
+    n_fwd = lib.evo_launch_count() - n_tok
+    assert n_tok == 1 and n_score == n_tok + n_fwd + 1            # fused head = the forward's last GEMM + one finishing kernel
