@@ -19,7 +19,7 @@ rng = np.random.default_rng(0)
 model = load_checkpoint("evo-1-8k-base", device=dev, random_init=True, seed=0)
 if what == "score":
     seqs = ["".join(rng.choice(list("ACGT"), size=8192)) for _ in range(8)]
-    for _ in range(3):
+    for _ in range(4):            # per pass the library launches: tokenize_pad, 129 x gemm_tcgen05_kernel (the last one = LSE epilogue), score_finish
         evo_b200.score_sequences(seqs, model, tok, device=dev)
 elif what == "gen":
     seqs = ["".join(rng.choice(list("ACGT"), size=1024)) for _ in range(16)]
