@@ -151,7 +151,7 @@ def _peer_attention(model, lib, pu, xn, mha, u, B, Lr, H, hd, rank, world, strea
     ap.k, ap.v, ap.kv_tok_stride, ap.kv_batch_stride = full.data_ptr() + dl * 2, full.data_ptr() + 2 * dl * 2, 3 * dl, L * 3 * dl
     ap.out_peers, ap.n_out_peers, ap.out_rows_per_peer, ap.out_row_stride, ap.out_col0 = C.cast(pu.ctx_ptrs, C.c_void_p), world, Lr, d, rank * dl
     causal_flops = 4.0 * pu.Hl * hd * (L * (L + 1) / 2.0)
-    model._record("attn", causal_flops, lambda: check(lib.evo_attn_fwd_ws(C.byref(ap), 2, None, 0, stream()), "evo_attn_fwd(peer)"))
+    model._record("attn", causal_flops, lambda: check(lib.evo_attn_fwd_ws(C.byref(ap), model.attn_variant, None, 0, stream()), "evo_attn_fwd(peer)"))
     pu.signal_and_wait(model, lib, "c", stream)
     return pu.ctx()
 
@@ -221,7 +221,9 @@ def sequence_parallel_forward(model, ids_local: torch.Tensor, rank: int, world: 
             # the transport is a collective decision: one rank on NCCL all-gathers while the others spin on peer flags would
             # hang, so every rank learns whether ALL of them have the peer path
             pu = None
-            if PEER_ULYSSES and pc is not None and B == 1 and H % world == 0 and model.attn_variant == 2 and model.fused_rope and model.gemm_variant in (0, 1):
+            has_bias = all(model.blocks[j].inner_mha_cls.Wqkv.bias is not None for j in model._attn_idxs)      # the rotary epilogue is bias + rotary
+            if (PEER_ULYSSES and pc is not None and B == 1 and H % world == 0 and hd == 128 and has_bias and model.attn_variant in (2, 3)
+                    and model.fused_rope and model.gemm_variant in (0, 1)):
                 try:
                     pu = PeerUlysses(world, rank, Lr, d, H, dev, group)
                 except Exception as ex:  # noqa
