@@ -446,3 +446,26 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "sample" in cb and abs(cb["value"] - d["value"]) < 1e-6
     assert d["e2e"] == {"value": d["value"], "unit": "nt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_helpers_assemble_the_contract_fields():
+    """bench.py's pure helpers: synthetic inputs are reproducible per seed, the roofline records carry the contract's keys and
+    consistent arithmetic (achieved = work / time, frac = achieved / peak), and the workloads are the BASELINE.json configs."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    a1, a2, a3 = b.synthetic_seqs(2, 50, seed=1), b.synthetic_seqs(2, 50, seed=1), b.synthetic_seqs(2, 50, seed=2)
+    assert a1 == a2 and a1 != a3 and set("".join(a1)) <= set("ACGT") and [len(s) for s in a1] == [50, 50]
+    assert b.WORKLOADS["8k"]["batch"] * b.WORKLOADS["8k"]["nt"] == 65536 and b.WORKLOADS["131k"]["nt"] == 131072 and b.WORKLOADS["gen"]["batch"] == 16
+    peaks = {"hbm_gbs": 6000.0, "bf16_tflops": 1600.0, "bf16_tflops_sustained": 1400.0, "source": "measured"}
+    by = {"gemm": [7.0e14, 500.0, 129.0], "hyena": [2.0e9 * 29, 29.0, 29.0], "attn": [1.4e13, 20.0, 3.0], "rmsnorm": [1.0, 10.0, 65.0]}
+    r = b.rooflines(by, 600.0, "8k", peaks)
+    g, h, at = r["roofline"], r["roofline_hyena"], r["roofline_attn"]
+    for rec, bound, unit in ((g, "tensor", "TFLOP/s"), (h, "hbm", "GB/s"), (at, "tensor", "TFLOP/s")):
+        for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert k in rec
+        assert rec["bound"] == bound and rec["unit"] == unit and abs(rec["frac"] - rec["achieved"] / rec["peak"]) < 1e-12
+    assert abs(g["achieved"] - 7.0e14 / 0.5 / 1e12) < 1e-6 and abs(h["achieved"] - 2.0e9 * 29 / 0.029 / 1e9) < 1e-6
+    assert abs(g["share_of_step"] - 500.0 / 600.0) < 1e-12 and g["launches_per_step"] == 129.0
