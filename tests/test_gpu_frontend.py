@@ -123,3 +123,24 @@ def test_public_scoring_entry_points_take_the_device_front_end_and_the_fused_hea
     real_forward(ids)
     n_fwd = lib.evo_launch_count() - n_tok
     assert n_tok == 1 and n_score == n_tok + n_fwd + 1            # fused head = the forward's last GEMM + one finishing kernel
+
+
+def test_cli_scripts_run_end_to_end_on_random_weights(tmp_path, capsys):
+    """python -m scripts.score / scripts.generate / scripts.example_inference with --random-init (no network on the GPU box): the
+    7B architecture is built on the device, the example FASTA is scored through the bucketed front-end, a short sample is generated."""
+    import scripts.example_inference as ex
+    import scripts.generate as gen
+    import scripts.score as sc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tsv = tmp_path / "scores.tsv"
+    scores = sc.main(["--input-fasta", os.path.join(root, "examples", "example_seqs.fasta"), "--output-tsv", str(tsv), "--model-name", "evo-1-8k-base",
+                      "--device", DEV, "--random-init"])
+    rows = tsv.read_text().strip().split("\n")
+    assert rows[0] == "seqs\tscores" and len(rows) == 4 and len(scores) == 3 and all(np.isfinite(scores))
+    assert [len(r.split("\t")[0]) for r in rows[1:]] == [4, 11, 32]
+    torch.cuda.empty_cache()
+    out, sc_ = gen.main(["--model-name", "evo-1-8k-base", "--prompt", "ACGTAC", "--n-samples", "2", "--n-tokens", "8", "--device", DEV, "--random-init", "--seed", "3", "--verbose", "0"])
+    assert len(out) == 2 and all(len(o) == 8 for o in out) and len(sc_) == 2
+    torch.cuda.empty_cache()
+    logits = ex.main(["--model-name", "evo-1-8k-base", "--device", DEV, "--random-init"])
+    assert tuple(logits.shape) == (3, 20, 512)

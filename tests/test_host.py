@@ -469,3 +469,23 @@ def test_bench_helpers_assemble_the_contract_fields():
         assert rec["bound"] == bound and rec["unit"] == unit and abs(rec["frac"] - rec["achieved"] / rec["peak"]) < 1e-12
     assert abs(g["achieved"] - 7.0e14 / 0.5 / 1e12) < 1e-6 and abs(h["achieved"] - 2.0e9 * 29 / 0.029 / 1e9) < 1e-6
     assert abs(g["share_of_step"] - 500.0 / 600.0) < 1e-12 and g["launches_per_step"] == 129.0
+
+
+def test_cli_scripts_keep_the_reference_arguments():
+    """scripts/score.py and scripts/generate.py: the reference's argument names and defaults (scripts/score.py:24-30,
+    scripts/generate.py:24-37 of evo-design/evo), plus the offline switches; the example FASTA parses to three sequences."""
+    import scripts.generate as g
+    import scripts.score as s
+    from evo_b200.frontend import read_fasta
+    a = vars(s.build_parser().parse_args(["--input-fasta", "in.fa", "--output-tsv", "out.tsv"]))
+    assert {k: a[k] for k in ("input_fasta", "output_tsv", "model_name", "batch_size", "device")} == \
+        {"input_fasta": "in.fa", "output_tsv": "out.tsv", "model_name": "evo-1-131k-base", "batch_size": 32, "device": "cuda:0"}
+    b = vars(g.build_parser().parse_args([]))
+    want = {"model_name": "evo-1-131k-base", "prompt": "ACGT", "n_samples": 3, "n_tokens": 100, "temperature": 1.0, "top_k": 4, "top_p": 1.0,
+            "cached_generation": True, "batched": True, "prepend_bos": False, "device": "cuda:0", "verbose": 1}
+    assert {k: b[k] for k in want} == want
+    with pytest.raises(SystemExit):
+        s.build_parser().parse_args([])                       # both paths are required, as in the reference
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names, seqs = read_fasta(os.path.join(root, "examples", "example_seqs.fasta"))
+    assert names == ["seq0", "seq1", "seq2"] and [len(x) for x in seqs] == [4, 11, 32] and set("".join(seqs)) <= set("ACGT")
