@@ -267,14 +267,31 @@ inline int ensure_dyn_smem(K kern, int bytes, unsigned long long& mask) {
   }
   return 0;
 }
-int pdl_level();         // evo_set_pdl(): 0 off, 1 all decode-step kernels, 2 weight-streaming GEMM only
+int pdl_level();         // evo_set_pdl(): 0 off, 1 all decode-step kernels, 2 weight-streaming GEMM only, 3 GEMM + the row-norm kernel
 
 // Programmatic dependent launch: every kernel that may be launched with the attribute calls pdl_wait() before it
 // first reads data written by (or writes data read by) the previous kernel; both are no-ops in a normal launch.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// host: kernel launch that adds the programmatic-serialization attribute when evo_set_pdl(1) is active
+// host: kernel launch that adds the programmatic-serialization attribute when evo_set_pdl(1) is active (or, for a kernel launched
+// through launch_pdl_light, at level 3 as well)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_at(int min_level_extra, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_level() == 1 || (min_level_extra > 0 && pdl_level() == min_level_extra)) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_light(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  return launch_pdl_at(3, kern, grid, block, smem, st, args...);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

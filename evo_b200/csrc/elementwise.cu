@@ -145,7 +145,7 @@ extern "C" int evo_rmsnorm(const void* x, const void* scale, void* out, int64_t 
   EVO_REQUIRE(D % 256 == 0 && D <= 8192, "evo_rmsnorm: D (%d) must be a multiple of 256 and <= 8192", D);
   if (rows == 0) return 0;
   if (rows <= 64) {
-    EVO_CUDA(launch_pdl(rmsnorm_row_kernel, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)scale, (uint4*)out,
+    EVO_CUDA(launch_pdl_light(rmsnorm_row_kernel, dim3((unsigned)rows), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (const uint4*)scale, (uint4*)out,
                         D / 8, (float)(1.0 / sqrt((double)D)), eps));
     return check_launch("evo_rmsnorm");
   }
