@@ -99,5 +99,5 @@ int evo_abi_version(void) { return 1; }
 int64_t evo_launch_count(void) { return evo::g_launches.load(); }
 void evo_reset_launch_count(void) { evo::g_launches.store(0); }
 void evo_note_graph_replay(int64_t launches) { evo::g_launches.fetch_add(launches); }
-int evo_set_pdl(int level) { return evo::g_pdl.exchange(level < 0 ? 0 : (level > 3 ? 3 : level)); }
+int evo_set_pdl(int level) { return evo::g_pdl.exchange(level < 0 ? 0 : (level > 4 ? 4 : level)); }
 }

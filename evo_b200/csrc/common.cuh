@@ -267,7 +267,7 @@ inline int ensure_dyn_smem(K kern, int bytes, unsigned long long& mask) {
   }
   return 0;
 }
-int pdl_level();         // evo_set_pdl(): 0 off, 1 all decode-step kernels, 2 weight-streaming GEMM only, 3 GEMM + the row-norm kernel
+int pdl_level();         // evo_set_pdl(): 0 off, 1 all decode-step kernels, 2 weight-streaming GEMM only, 3 + the row-norm kernel, 4 + hyena_step
 
 // Programmatic dependent launch: every kernel that may be launched with the attribute calls pdl_wait() before it
 // first reads data written by (or writes data read by) the previous kernel; both are no-ops in a normal launch.
@@ -281,7 +281,7 @@ inline cudaError_t launch_pdl_at(int min_level_extra, void (*kern)(KArgs...), di
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  if (pdl_level() == 1 || (min_level_extra > 0 && pdl_level() == min_level_extra)) {
+  if (pdl_level() == 1 || (min_level_extra > 0 && pdl_level() >= min_level_extra)) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;

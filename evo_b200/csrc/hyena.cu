@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) hyena_step_kernel(const bf16* __restrict_
                                   float* __restrict__ state, const bf16* __restrict__ fir_w, const bf16* __restrict__ fir_b,
                                   const bf16* __restrict__ Dskip, const float* __restrict__ poles, const float* __restrict__ residues,
                                   int B, int D, int hd) {
-  pdl_launch_dependents(); pdl_wait();
+  pdl_launch_dependents();
   static_assert(NS == 8, "one lane per modal state");
   const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (b, channel, s); B*D*8 is a multiple of 256
   const int s = (int)(gidx & 7);
@@ -241,26 +241,33 @@ __global__ void __launch_bounds__(256) hyena_step_kernel(const bf16* __restrict_
   const int b = (int)(idx / D), ch = (int)(idx % D);
   const int head = ch / hd, o = ch % hd;
   const int base = (threadIdx.x & 31) & ~7;
-  // modal operands first: their latency overlaps the FIR
+  // Everything except u is older than the previous kernel (filter parameters; the states this kernel itself wrote one token ago),
+  // so it is fetched BEFORE griddepcontrol.wait: under programmatic dependent launch these loads overlap the in-projection's tail.
   const float2 p = reinterpret_cast<const float2*>(poles)[(long long)ch * NS + s];
   const float2 r = reinterpret_cast<const float2*>(residues)[(long long)ch * NS + s];
   float2* st = reinterpret_cast<float2*>(state) + idx * NS + s;
   const float2 sv = *st;
   const float dskip = __bfloat162float(Dskip[ch]);
+  const long long C3 = 3LL * D;
+  const long long c = (long long)head * 3 * hd + (long long)(s < 3 ? s : 0) * hd + o;            // x2, x1, v (lanes 0..2)
+  bf16* fs = fir_state + (b * C3 + c) * 2;
+  bf16 s0_b = __float2bfloat16_rn(0.f), s1_b = s0_b;
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f, fb = 0.f;
+  if (s < 3) {
+    s0_b = fs[0]; s1_b = fs[1];
+    w0 = __bfloat162float(fir_w[c * 3 + 0]); w1 = __bfloat162float(fir_w[c * 3 + 1]); w2 = __bfloat162float(fir_w[c * 3 + 2]);
+    fb = __bfloat162float(fir_b[c]);
+  }
+  pdl_wait();
   float f = 0.f;
   if (s < 3) {
-    const long long C3 = 3LL * D;
-    const long long c = (long long)head * 3 * hd + (long long)s * hd + o;            // x2, x1, v
     const bf16 un_b = u[b * C3 + c];
     const float un = __bfloat162float(un_b);
-    bf16* fs = fir_state + (b * C3 + c) * 2;
-    const bf16 s1_b = fs[1];
-    const float s0 = __bfloat162float(fs[0]), s1 = __bfloat162float(s1_b);
-    const float w0 = __bfloat162float(fir_w[c * 3 + 0]), w1 = __bfloat162float(fir_w[c * 3 + 1]), w2 = __bfloat162float(fir_w[c * 3 + 2]);
+    const float s0 = __bfloat162float(s0_b), s1 = __bfloat162float(s1_b);
     // y = h0*u + sum(fir_state*h) + bias, bf16 tensor ops: each product / sum rounds (rp)
     const float t0 = rbf(w2 * un);
     const float t1 = rbf(rbf(s0 * w0) + rbf(s1 * w1));          // torch.sum over two bf16 products (fp32 accumulate, rp)
-    f = rbf(rbf(t0 + t1) + __bfloat162float(fir_b[c]));
+    f = rbf(rbf(t0 + t1) + fb);
     fs[0] = s1_b; fs[1] = un_b;
   }
   const float x2 = __shfl_sync(0xffffffffu, f, base + 0);
@@ -415,7 +422,7 @@ extern "C" int evo_hyena_step(const void* u, void* y, void* fir_state, float* st
   long long n = (long long)B * D * NS;
   if (n == 0) return 0;
   EVO_REQUIRE(D % 32 == 0, "evo_hyena_step: D (%d) must be a multiple of 32", D);
-  EVO_CUDA(launch_pdl(hyena_step_kernel, dim3((unsigned)(n / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)u, (bf16*)y, (bf16*)fir_state, state,
+  EVO_CUDA(launch_pdl_at(4, hyena_step_kernel, dim3((unsigned)(n / 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)u, (bf16*)y, (bf16*)fir_state, state,
       (const bf16*)fir_w, (const bf16*)fir_b, (const bf16*)Dskip, poles, residues, B, D, D / nheads));
   return check_launch("evo_hyena_step");
 }

@@ -209,7 +209,7 @@ class StripedHyena(nn.Module):
         # decode-step GEMMs: stream-K weight-streaming kernel (csrc/gemm_smallm.cu) for batch <= 64; "0" = the 128x64 tiles
         self.decode_streamk = os.environ.get("EVO_B200_DECODE_STREAMK", "1") != "0"
         # programmatic dependent launch inside a decode step (evo_set_pdl): 0 off, 1 every kernel, 2 weight-streaming GEMMs only
-        self.decode_pdl = int(os.environ.get("EVO_B200_DECODE_PDL", "2"))
+        self.decode_pdl = int(os.environ.get("EVO_B200_DECODE_PDL", "4"))
         # the Hyena decode step inside the in-projection GEMM's epilogue (EVO_EPI_HYENA_STEP).  Bit-identical to the separate
         # evo_hyena_step launch but SLOWER on B200 (5.12 vs 4.30 ms/step at batch 16, profiles/r02_decode_fused_step_call8.txt): the
         # step of a tile runs on the 128 epilogue threads of its last contributor -- 16 batch rows x 8 states of dependent

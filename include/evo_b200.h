@@ -112,7 +112,8 @@ size_t evo_gemm_smallm_workspace(int64_t M, int64_t N, int64_t K, int epilogue);
 int evo_gemm_smallm(const evo_gemm_smallm_params* p, void* stream);
 /* Programmatic dependent launch for the decode step.  0 = off (default); 1 = every decode-step kernel is launched with
  * programmatic stream serialization; 2 = only evo_gemm_smallm is (its weight prefetch then overlaps the small kernel or
- * the GEMM tail in front of it); 3 = evo_gemm_smallm and the few-row evo_rmsnorm.  Every decode-step kernel begins with griddepcontrol.launch_dependents and waits
+ * the GEMM tail in front of it); 3 = evo_gemm_smallm and the few-row evo_rmsnorm; 4 = those and
+ * evo_hyena_step (which fetches its filter parameters and states ahead of the wait).  Every decode-step kernel begins with griddepcontrol.launch_dependents and waits
  * (griddepcontrol.wait) before it first touches dependent data.  Process-wide switch; returns the previous value. */
 int evo_set_pdl(int level);
 

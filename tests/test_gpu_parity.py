@@ -634,13 +634,14 @@ def test_decode_streamk_pdl_paths_agree():
         c2 = run(True, 1, True)
         e = run(True, 2, True)
         f3 = run(True, 3, True)
+        f4 = run(True, 4, True)
     finally:
         m.decode_streamk, m.decode_pdl, m.decode_graph = saved
         m._decode = None
     scale = a.float().abs().max().item()
     assert maxerr(b, a) <= 0.03 * scale and maxerr(c, a) <= 0.03 * scale
     assert torch.equal(c, c2)
-    assert torch.equal(b, c) and torch.equal(b, e) and torch.equal(b, f3)        # PDL and graph replay change scheduling only
+    assert torch.equal(b, c) and torch.equal(b, e) and torch.equal(b, f3) and torch.equal(b, f4)        # PDL and graph replay change scheduling only
 
 
 def test_decode_fused_hyena_step_epilogue_is_bit_identical():
