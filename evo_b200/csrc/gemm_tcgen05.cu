@@ -65,6 +65,7 @@ struct GemmArgs {
   const long long* targets;   // EPI_LSE only: (M) target token per row (-1: none)
   float4* part;               // EPI_LSE only: (M, n_blocks) per-row partial statistics {max, sum e^(x-max), sum e^(x-max) x, target logit}
   int l2_hints;          // TMA loads carry L2 eviction priorities (resident slab evict_last, streaming operand evict_first)
+  int skew;              // experiment (EVO_B200_GEMM_SKEW): the producer of tile slot t starts t * skew cycles late
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
 
@@ -242,6 +243,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint64_t keep = l2_policy_evict_last(), first = g.l2_hints == 1 ? l2_policy_evict_first() : l2_policy_evict_normal();
       const uint64_t pol_a = g.raster_n ? first : keep;
       const uint64_t pol_b = g.raster_n ? keep : first;
+      if (g.skew > 0) {      // de-phase the CTAs that share operand tiles: the first of them misses, the others find the tile in L2
+        const long long t0 = clock64(), wait = (long long)tile0 * g.skew;
+        while (clock64() - t0 < wait) __nanosleep(64);
+      }
       for (int tile = tile0; tile < n_tiles; tile += tile_step) {
         int m_blk, n_blk; tile_coords(tile, g, m_blk, n_blk);
         const int a_row = (m_blk * CG + (int)cta_rank) * BM;
@@ -437,6 +442,8 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
     g.group_m = g.raster_n ? gn : gm;
     static const char* env_h = getenv("EVO_B200_GEMM_L2_HINTS");   // experiments only: 0 (default) plain TMA loads, 1 / 2 see the producer
     g.l2_hints = (BN == BN_BIG && env_h) ? atoi(env_h) : 0;
+    const char* env_s = getenv("EVO_B200_GEMM_SKEW");               // experiments only (read per launch)
+    g.skew = (BN == BN_BIG && env_s) ? atoi(env_s) : 0;
     const char* env_g = getenv("EVO_B200_GEMM_GROUP");      // experiments only (read per launch: tools/gemm_raster_sweep.py changes them)
     const char* env_r = getenv("EVO_B200_GEMM_RASTER_N");
     if (env_r) g.raster_n = atoi(env_r);

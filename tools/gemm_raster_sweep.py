@@ -21,6 +21,14 @@ CONFIGS = {
     "proj": [None, (1, 4), (1, 9), (1, 24), (1, 48), (0, 4), (0, 9), (0, 19), (0, 37)],
     "out": [None, (1, 4), (1, 16), (0, 9), (0, 37)],
 }
+SKEWS = [0, 128, 512, 2048, 8192]       # --skew: default grouping, producer start skew in cycles per tile slot
+if "--skew" in sys.argv:
+    SHAPES = SHAPES[:3]
+    CONFIGS = {name: [("skew", c) for c in SKEWS] for name, _, _, _ in SHAPES}
+
+
+def label(cfg):
+    return "default" if cfg is None else ("skew=%d cycles/slot" % cfg[1] if cfg[0] == "skew" else "raster_n=%d group=%d" % cfg)
 
 
 def order():
@@ -50,7 +58,7 @@ def table(path):
     for i, (name, cfg) in zip(ids, order()):
         m = per[i]
         b = m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]
-        print(f"{name:5s} {'default' if cfg is None else 'raster_n=%d group=%d' % cfg:22s} {b / 1e9:7.2f} GB = {b / algorithmic(name):5.2f}x algorithmic   {m['gpu__time_duration.sum']:9.1f} us")
+        print(f"{name:5s} {label(cfg):22s} {b / 1e9:7.2f} GB = {b / algorithmic(name):5.2f}x algorithmic   {m['gpu__time_duration.sum']:9.1f} us")
 
 
 def main():
@@ -72,9 +80,11 @@ def main():
                             residual=resid.data_ptr() if epi in (2, 3) else None, ldr=n_out, M=M, N=N, K=K, epilogue=epi, variant=0)
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for cfg in CONFIGS[name]:
-            for k in ("EVO_B200_GEMM_RASTER_N", "EVO_B200_GEMM_GROUP"):
+            for k in ("EVO_B200_GEMM_RASTER_N", "EVO_B200_GEMM_GROUP", "EVO_B200_GEMM_SKEW"):
                 os.environ.pop(k, None)
-            if cfg is not None:
+            if cfg is not None and cfg[0] == "skew":
+                os.environ["EVO_B200_GEMM_SKEW"] = str(cfg[1])
+            elif cfg is not None:
                 os.environ["EVO_B200_GEMM_RASTER_N"], os.environ["EVO_B200_GEMM_GROUP"] = str(cfg[0]), str(cfg[1])
             if under_ncu:
                 _lib.check(lib.evo_gemm(C.byref(p), st), "evo_gemm")
@@ -89,13 +99,13 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             t = sorted(ts[1:])[1]
-            print(f"{name:5s} {'default' if cfg is None else 'raster_n=%d group=%d' % cfg:22s} {t * 1e3:9.1f} us  {2.0 * M * N * K / t / 1e9:7.1f} TFLOP/s", flush=True)
+            print(f"{name:5s} {label(cfg):22s} {t * 1e3:9.1f} us  {2.0 * M * N * K / t / 1e9:7.1f} TFLOP/s", flush=True)
         del a, w, resid, out
     torch.cuda.synchronize()
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 2 and sys.argv[1] == "--table":
-        table(sys.argv[2])
+    if "--table" in sys.argv:
+        table(sys.argv[sys.argv.index("--table") + 1])
     else:
         main()
