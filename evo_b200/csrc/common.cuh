@@ -242,6 +242,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
 
 // cluster helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t ld_shared_cluster_u32(const void* p, uint32_t cta) {     // the same smem offset in CTA `cta` of the cluster
+  uint32_t v;
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %1, %2;\n\tld.shared::cluster.u32 %0, [ra];\n\t}\n" : "=r"(v) : "r"(smem_u32(p)), "r"(cta) : "memory");
+  return v;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -254,6 +259,11 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
                       const uint32_t* box, bool swizzle128);
 
 int device_sm_count();     // of the CURRENT device (cached per device ordinal)
+
+// SM -> die map of the current device (die_map.cu), measured on first use; nullptr when it could not be established (or when
+// `caller` is capturing and the device has not been calibrated yet).  tab[smid >> 1] = die | (rank of this TPC within its die << 1).
+struct DieMap { bool valid = false; int pairs[2] = {0, 0}; const uint16_t* tab = nullptr; };
+const DieMap* die_map(cudaStream_t caller);
 int current_device();      // cudaGetDevice, -1 on error
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: `mask` keeps one "done" bit per device

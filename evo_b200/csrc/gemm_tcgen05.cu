@@ -65,6 +65,8 @@ struct GemmArgs {
   const long long* targets;   // EPI_LSE only: (M) target token per row (-1: none)
   float4* part;               // EPI_LSE only: (M, n_blocks) per-row partial statistics {max, sum e^(x-max), sum e^(x-max) x, target logit}
   int l2_hints;          // TMA loads carry L2 eviction priorities (resident slab evict_last, streaming operand evict_first)
+  const uint16_t* die_tab;   // die-aware rasterisation (CG == 2): tab[smid >> 1] = die | slot << 1, nullptr = off
+  int m_split, die_pairs0, die_pairs1;   // die 0 owns row-blocks [0, m_split) with die_pairs0 CTA pairs, die 1 the rest
   int skew;              // experiment (EVO_B200_GEMM_SKEW): the producer of tile slot t starts t * skew cycles late
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
@@ -74,16 +76,17 @@ constexpr int EPI_LSE = 5;     // internal: scoring epilogue (evo_unembed_score)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // grouped rasterisation: GROUP_M row-blocks share the sweep over n so their A tiles stay in L2
-__device__ __forceinline__ void tile_coords(int tile, const GemmArgs& g, int& m_blk, int& n_blk) {
-  const int major = g.raster_n ? g.n_blocks : g.m_blocks;     // the grouped dimension
-  const int minor = g.raster_n ? g.m_blocks : g.n_blocks;     // the swept dimension
+// (over the row-blocks [m_lo, m_lo + m_cnt): the whole matrix, or the share of one die)
+__device__ __forceinline__ void tile_coords(int tile, const GemmArgs& g, int m_lo, int m_cnt, int& m_blk, int& n_blk) {
+  const int major = g.raster_n ? g.n_blocks : m_cnt;     // the grouped dimension
+  const int minor = g.raster_n ? m_cnt : g.n_blocks;     // the swept dimension
   int per_group = g.group_m * minor;
   int grp = tile / per_group;
   int first = grp * g.group_m;
   int gsz = min(g.group_m, major - first);
   int in = tile - grp * per_group;
   int a = first + in % gsz, b = in / gsz;
-  m_blk = g.raster_n ? b : a;
+  m_blk = m_lo + (g.raster_n ? b : a);
   n_blk = g.raster_n ? a : b;
 }
 
@@ -206,12 +209,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = empty + C_::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* walk_slot = tmem_slot + 2;          // pair leader: die | slot << 1 of this pair (die-aware rasterisation)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if constexpr (CG == 2) {
+    if (g.die_tab != nullptr && warp == 3 && lane == 0 && leader) {
+      uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      *walk_slot = g.die_tab[sm >> 1];
+    }
+  }
   if (warp == 1 && lane == 0) {
     // full: one arrival (the leader's arrive.expect_tx); the byte count covers both CTAs' loads
     for (int i = 0; i < C_::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -226,9 +236,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_tiles = g.m_blocks * g.n_blocks;           // m_blocks counts (BM*CG)-row blocks
-  const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // Tile walk of this CTA (pair): tiles w_first, w_first + w_step, ... < n_tiles of the row-blocks [m_lo, m_lo + m_cnt).
+  // Die-aware (CG == 2, full grid): each die works on its own contiguous share of the row-blocks, so the streamed operand's
+  // tiles are fetched by one die's L2 only; the pair's (die, slot) comes from the leader's %smid and is read by BOTH CTAs from the
+  // leader's shared memory, so the two can never disagree about the walk.
+  int w_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // m_blocks counts (BM*CG)-row blocks
+  int w_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  int m_lo = 0, m_cnt = g.m_blocks;
+  if constexpr (CG == 2) {
+    if (g.die_tab != nullptr) {
+      const uint32_t v = ld_shared_cluster_u32(walk_slot, 0);
+      const int die = (int)(v & 1u);
+      w_first = (int)(v >> 1);
+      w_step = die ? g.die_pairs1 : g.die_pairs0;
+      m_lo = die ? g.m_split : 0;
+      m_cnt = die ? g.m_blocks - g.m_split : g.m_split;
+    }
+  }
+  const int tile0 = w_first, tile_step = w_step;
+  const int n_tiles = m_cnt * g.n_blocks;
   const int nkb = (int)(g.K / (BK * KSUB));
 
   if (warp == 0) {
@@ -248,7 +274,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         while (clock64() - t0 < wait) __nanosleep(64);
       }
       for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-        int m_blk, n_blk; tile_coords(tile, g, m_blk, n_blk);
+        int m_blk, n_blk; tile_coords(tile, g, m_lo, m_cnt, m_blk, n_blk);
         const int a_row = (m_blk * CG + (int)cta_rank) * BM;
         const int b_row = n_blk * BN + (int)cta_rank * C_::B_ROWS;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -314,7 +340,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp - EPI_WARP0;                      // == warp % 4: the TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-      int m_blk, n_blk; tile_coords(tile, g, m_blk, n_blk);
+      int m_blk, n_blk; tile_coords(tile, g, m_lo, m_cnt, m_blk, n_blk);
       const long long row = (long long)(m_blk * CG + (int)cta_rank) * BM + q * 32 + lane;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -459,8 +485,26 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
   cfg.dynamicSmemBytes = C_::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
+  g.die_tab = nullptr; g.m_split = 0; g.die_pairs0 = g.die_pairs1 = 0;
   if (CG == 2) {
     int pairs = min(n_tiles, sms / 2);
+    // Die-aware rasterisation (EVO_B200_GEMM_DIE_RASTER, see the kernel's tile walk): a full grid of pairs, enough row-blocks
+    // for both dies, and a self-consistent SM -> die map of this device.  m_split balances the two dies' wave counts.
+    const char* env_d = getenv("EVO_B200_GEMM_DIE_RASTER");          // read per launch (tools/gemm_raster_sweep.py toggles it)
+    if (BN == BN_BIG && env_d && atoi(env_d) != 0 && pairs == sms / 2 && g.m_blocks >= 32) {
+      const DieMap* dm = die_map(st);
+      if (dm && dm->pairs[0] + dm->pairs[1] == pairs) {
+        const double prop = (double)g.m_blocks * dm->pairs[0] / pairs;
+        long long best = -1; int best_ms = 0;
+        for (int ms = std::max(1, (int)prop - 2); ms <= std::min(g.m_blocks - 1, (int)prop + 3); ++ms) {
+          const long long w0 = ((long long)ms * g.n_blocks + dm->pairs[0] - 1) / dm->pairs[0];
+          const long long w1 = ((long long)(g.m_blocks - ms) * g.n_blocks + dm->pairs[1] - 1) / dm->pairs[1];
+          const long long w = std::max(w0, w1) * 1024 + (long long)(std::fabs(ms - prop) * 16);     // fewest waves, then closest to proportional
+          if (best < 0 || w < best) { best = w; best_ms = ms; }
+        }
+        g.die_tab = dm->tab; g.m_split = best_ms; g.die_pairs0 = dm->pairs[0]; g.die_pairs1 = dm->pairs[1];
+      }
+    }
     cfg.gridDim = dim3(pairs * 2);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;

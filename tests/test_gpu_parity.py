@@ -349,6 +349,39 @@ def test_gemm_all_epilogues(variant, M, N, K):
     assert (out == ref).float().mean() > (0.97 if K <= 1024 else 0.88)
 
 
+def test_gemm_die_aware_walk_is_bit_identical(tmp_path, monkeypatch):
+    """EVO_B200_GEMM_DIE_RASTER=1: each die of the GPU takes its own share of the row-blocks (csrc/die_map.cu measures which SM is on
+    which die).  Only the order in which tiles are visited changes: every epilogue must give the same bits as the default walk, on
+    a shape with a ragged last row-block, more tiles than CTA pairs and both grouping directions."""
+    dump = tmp_path / "die_map.txt"
+    monkeypatch.setenv("EVO_B200_GEMM_DIE_DUMP", str(dump))
+    torch.manual_seed(5)
+    for M, N, K in [(8200, 1024, 256), (16500, 512, 128), (9000, 2560, 64)]:
+        a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+        w = (torch.randn(N, K, device=DEV) / math.sqrt(K)).bfloat16()
+        bias = (torch.randn(N, device=DEV) * 0.2).bfloat16()
+        resid = torch.randn(M, N, device=DEV).bfloat16()
+        for raster in (None, "0", "1"):
+            if raster is None:
+                monkeypatch.delenv("EVO_B200_GEMM_RASTER_N", raising=False)
+            else:
+                monkeypatch.setenv("EVO_B200_GEMM_RASTER_N", raster)
+            outs = {}
+            for die in ("0", "1"):
+                monkeypatch.setenv("EVO_B200_GEMM_DIE_RASTER", die)
+                outs[die] = [G._gemm(a, w, M, N, K, _lib.EPI_NONE, 0), G._gemm(a, w, M, N, K, _lib.EPI_BIAS_RESID, 0, bias=bias, resid=resid),
+                             G._gemm(a, w, M, N, K, _lib.EPI_GELU_GATE, 0, ldc=N // 2)]
+            for x, y in zip(outs["0"], outs["1"]):
+                assert not torch.isnan(y.float()).any()
+                assert torch.equal(x, y)
+    monkeypatch.delenv("EVO_B200_GEMM_RASTER_N", raising=False)
+    text = dump.read_text() if dump.exists() else ""
+    if not text.startswith("# ok"):
+        pytest.skip("the SM -> die calibration was rejected on this GPU (%s): the die-aware walk stayed off" % (text.splitlines()[0] if text else "no dump"))
+    dies = [int(line.split()[1]) for line in text.splitlines() if line and not line.startswith("#")]
+    assert len(dies) == torch.cuda.get_device_properties(0).multi_processor_count and min(dies.count(0), dies.count(1)) >= len(dies) // 4
+
+
 def test_gemm_tile_major_weights_variant3():
     """variant 3 = variant 2 reading W tile-major; must give exactly the same bits as variant 2."""
     torch.manual_seed(0)

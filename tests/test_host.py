@@ -489,3 +489,51 @@ def test_cli_scripts_keep_the_reference_arguments():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     names, seqs = read_fasta(os.path.join(root, "examples", "example_seqs.fasta"))
     assert names == ["seq0", "seq1", "seq2"] and [len(x) for x in seqs] == [4, 11, 32] and set("".join(seqs)) <= set("ACGT")
+
+
+def test_die_classifier_on_synthetic_latencies(tmp_path):
+    """csrc/die_classify.h (the host half of the SM -> die calibration): recovers a 70 / 78 split from latencies with per-SM and
+    per-line offsets, clock drift and noise; refuses to answer without a two-group structure or when a CTA pair straddles TPCs."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "die_classify.h"
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+int main(int argc, char** argv) {
+  const int sms = 148, P = 24;
+  const double gap = atof(argv[1]), noise = atof(argv[2]);
+  const int bad_pair = atoi(argv[3]);
+  std::mt19937 rng(atoi(argv[4]));
+  std::normal_distribution<double> nd(0.0, 1.0);
+  std::vector<int> truth(sms);
+  for (int t = 0; t < 74; ++t) { int d = (t < 18 || (t >= 37 && t < 54)) ? 0 : 1; truth[2 * t] = truth[2 * t + 1] = d; }
+  std::vector<int> home(P); for (int p = 0; p < P; ++p) home[p] = rng() & 1;
+  std::vector<float> lat(sms * P);
+  for (int s = 0; s < sms; ++s) {
+    const double off = 8 * nd(rng), scale = 1.0 + 0.05 * s / sms;
+    for (int p = 0; p < P; ++p) lat[s * P + p] = (float)(scale * (234 + off + 3 * std::sin(p) + (truth[s] != home[p] ? gap : 0.0)) + noise * nd(rng));
+  }
+  std::vector<unsigned> where(sms);
+  for (int b = 0; b < sms; ++b) where[b] = (unsigned)((b + 142) % sms) | ((b & 1) << 16);
+  if (bad_pair) std::swap(where[3], where[5]);
+  std::vector<int> die;
+  const char* why = evo::classify_dies(lat, sms, P, where, die);
+  if (why) { printf("REJECT %s\n", why); return 0; }
+  int wrong = 0, n0 = 0; for (int s = 0; s < sms; ++s) { wrong += die[s] != (truth[s] ^ truth[0]); n0 += die[s] == 0; }
+  printf("OK wrong=%d die0=%d\n", wrong, n0);
+}
+''')
+    exe = tmp_path / "t"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "evo_b200", "csrc"), str(src), "-o", str(exe)], check=True)
+    run = lambda *a: subprocess.run([str(exe), *map(str, a)], capture_output=True, text=True, check=True).stdout.strip()
+    for seed in (1, 2, 3):
+        assert run(28, 2, 0, seed) == "OK wrong=0 die0=70"
+    assert run(12, 3, 0, 4) == "OK wrong=0 die0=70"
+    assert run(0, 2, 0, 1).startswith("REJECT no dominant")
+    assert run(28, 25, 0, 1).startswith("REJECT")
+    assert run(28, 2, 1, 1).startswith("REJECT a CTA pair")

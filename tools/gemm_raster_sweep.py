@@ -25,10 +25,18 @@ SKEWS = [0, 128, 512, 2048, 8192]       # --skew: default grouping, producer sta
 if "--skew" in sys.argv:
     SHAPES = SHAPES[:3]
     CONFIGS = {name: [("skew", c) for c in SKEWS] for name, _, _, _ in SHAPES}
+if "--die" in sys.argv:                  # --die: default grouping, die-oblivious vs die-aware tile walk
+    CONFIGS = {name: [("die", 0), ("die", 1), ("die", 0), ("die", 1)] for name, _, _, _ in SHAPES}
 
 
 def label(cfg):
-    return "default" if cfg is None else ("skew=%d cycles/slot" % cfg[1] if cfg[0] == "skew" else "raster_n=%d group=%d" % cfg)
+    if cfg is None:
+        return "default"
+    if cfg[0] == "skew":
+        return "skew=%d cycles/slot" % cfg[1]
+    if cfg[0] == "die":
+        return "die-aware walk" if cfg[1] else "die-oblivious walk"
+    return "raster_n=%d group=%d" % cfg
 
 
 def order():
@@ -84,6 +92,8 @@ def main():
                 os.environ.pop(k, None)
             if cfg is not None and cfg[0] == "skew":
                 os.environ["EVO_B200_GEMM_SKEW"] = str(cfg[1])
+            elif cfg is not None and cfg[0] == "die":
+                os.environ["EVO_B200_GEMM_DIE_RASTER"] = str(cfg[1])
             elif cfg is not None:
                 os.environ["EVO_B200_GEMM_RASTER_N"], os.environ["EVO_B200_GEMM_GROUP"] = str(cfg[0]), str(cfg[1])
             if under_ncu:
