@@ -262,8 +262,12 @@ int device_sm_count();     // of the CURRENT device (cached per device ordinal)
 
 // SM -> die map of the current device (die_map.cu), measured on first use; nullptr when it could not be established (or when
 // `caller` is capturing and the device has not been calibrated yet).  tab[smid >> 1] = die | (rank of this TPC within its die << 1).
-struct DieMap { bool valid = false; int pairs[2] = {0, 0}; const uint16_t* tab = nullptr; };
+struct DieMap {
+  static constexpr int CLAIM_LINES = 256, CLAIM_WORDS = 128;     // per-launch slot-claim words of the die-aware GEMM walk
+  bool valid = false; int pairs[2] = {0, 0}; const uint16_t* tab = nullptr; unsigned* claims = nullptr;
+};
 const DieMap* die_map(cudaStream_t caller);
+unsigned* die_next_claims(const DieMap* dm);       // the next line of dm->claims (round robin per device); the caller zeroes it in stream order
 int current_device();      // cudaGetDevice, -1 on error
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: `mask` keeps one "done" bit per device

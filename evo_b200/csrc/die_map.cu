@@ -13,6 +13,7 @@
 #include "die_classify.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -62,7 +63,7 @@ __global__ void pair_probe_kernel(unsigned* where) {
   if (threadIdx.x == 0) { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); where[blockIdx.x] = smid() | (r << 16); }
 }
 
-struct Entry { std::once_flag once; DieMap map; };
+struct Entry { std::once_flag once; DieMap map; std::atomic<unsigned> next_line{0}; };
 Entry g_entries[64];
 
 void dump(const char* path, int sms, const std::vector<float>& lat, const std::vector<int>& die, const char* verdict) {
@@ -132,7 +133,11 @@ bool calibrate(DieMap& out) {
   uint16_t* tab_d = nullptr;
   if (cudaMalloc(&tab_d, tab.size() * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); return false; }
   if (cudaMemcpy(tab_d, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(tab_d); cudaGetLastError(); return false; }
-  out.valid = true; out.pairs[0] = next[0]; out.pairs[1] = next[1]; out.tab = tab_d;
+  unsigned* claims = nullptr;
+  if (next[0] + next[1] > DieMap::CLAIM_WORDS || cudaMalloc(&claims, (size_t)DieMap::CLAIM_LINES * DieMap::CLAIM_WORDS * sizeof(unsigned)) != cudaSuccess) {
+    cudaFree(tab_d); cudaGetLastError(); return false;
+  }
+  out.valid = true; out.pairs[0] = next[0]; out.pairs[1] = next[1]; out.tab = tab_d; out.claims = claims;
   return true;
 }
 
@@ -151,4 +156,10 @@ const DieMap* evo::die_map(cudaStream_t caller) {
   }
   std::call_once(e.once, [&] { e.map = DieMap{}; calibrate(e.map); });
   return e.map.valid ? &e.map : nullptr;
+}
+
+unsigned* evo::die_next_claims(const DieMap* dm) {
+  for (Entry& e : g_entries)
+    if (&e.map == dm) return dm->claims + (size_t)(e.next_line.fetch_add(1) % DieMap::CLAIM_LINES) * DieMap::CLAIM_WORDS;
+  return dm->claims;
 }

@@ -66,7 +66,9 @@ struct GemmArgs {
   float4* part;               // EPI_LSE only: (M, n_blocks) per-row partial statistics {max, sum e^(x-max), sum e^(x-max) x, target logit}
   int l2_hints;          // TMA loads carry L2 eviction priorities (resident slab evict_last, streaming operand evict_first)
   const uint16_t* die_tab;   // die-aware rasterisation (CG == 2): tab[smid >> 1] = die | slot << 1, nullptr = off
+  unsigned* die_claim;       // one word per (die, slot), zeroed before the launch: a pair owns the slot it sets first
   int m_split, die_pairs0, die_pairs1;   // die 0 owns row-blocks [0, m_split) with die_pairs0 CTA pairs, die 1 the rest
+  int die_collide;           // test hook: every pair asks for the same slot first
   int skew;              // experiment (EVO_B200_GEMM_SKEW): the producer of tile slot t starts t * skew cycles late
   int raster_n;          // 0: groups of `group_m` row-blocks sweep all of N (A stays in L2); 1: groups of `group_m` column-blocks sweep all of M (W stays in L2)
 };
@@ -218,8 +220,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if constexpr (CG == 2) {
     if (g.die_tab != nullptr && warp == 3 && lane == 0 && leader) {
+      // The slot this TPC would like (its rank among the TPCs of its die), then a claim: if the slot is taken -- two pairs ran on
+      // one TPC one after the other because something else held an SM when the grid started -- take the next free one.  As many
+      // slots as pairs, so every slot ends up owned exactly once whatever the placement was.
       uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-      *walk_slot = g.die_tab[sm >> 1];
+      const uint32_t want = g.die_collide ? 0u : g.die_tab[sm >> 1];
+      const int total = g.die_pairs0 + g.die_pairs1;
+      int idx = (int)(want >> 1) + ((want & 1u) ? g.die_pairs0 : 0);
+      for (int k = 0; k < total && atomicCAS(&g.die_claim[idx], 0u, 1u) != 0u; ++k) idx = idx + 1 == total ? 0 : idx + 1;
+      const uint32_t die = idx >= g.die_pairs0 ? 1u : 0u;
+      *walk_slot = die | (uint32_t)(die ? idx - g.die_pairs0 : idx) << 1;
     }
   }
   if (warp == 1 && lane == 0) {
@@ -485,13 +495,15 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
   cfg.dynamicSmemBytes = C_::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  g.die_tab = nullptr; g.m_split = 0; g.die_pairs0 = g.die_pairs1 = 0;
+  g.die_tab = nullptr; g.die_claim = nullptr; g.m_split = 0; g.die_pairs0 = g.die_pairs1 = 0; g.die_collide = 0;
   if (CG == 2) {
     int pairs = min(n_tiles, sms / 2);
-    // Die-aware rasterisation (EVO_B200_GEMM_DIE_RASTER, see the kernel's tile walk): a full grid of pairs, enough row-blocks
-    // for both dies, and a self-consistent SM -> die map of this device.  m_split balances the two dies' wave counts.
+    // Die-aware rasterisation (see the kernel's tile walk; EVO_B200_GEMM_DIE_RASTER=0 turns it off, 2 is a test hook): a full
+    // grid of pairs, enough row-blocks for both dies, and a self-consistent SM -> die map of this device.  m_split balances the two
+    // dies' wave counts.  In-step +2.0 / +2.7 % on the 8k workload (profiles/r02_gemm_die_raster_call28.txt).
     const char* env_d = getenv("EVO_B200_GEMM_DIE_RASTER");          // read per launch (tools/gemm_raster_sweep.py toggles it)
-    if (BN == BN_BIG && env_d && atoi(env_d) != 0 && pairs == sms / 2 && g.m_blocks >= 32) {
+    const int die_mode = env_d ? atoi(env_d) : 1;
+    if (BN == BN_BIG && die_mode != 0 && pairs == sms / 2 && g.m_blocks >= 32) {
       const DieMap* dm = die_map(st);
       if (dm && dm->pairs[0] + dm->pairs[1] == pairs) {
         const double prop = (double)g.m_blocks * dm->pairs[0] / pairs;
@@ -502,7 +514,11 @@ int launch(const evo_gemm_params* p, cudaStream_t st, const long long* targets =
           const long long w = std::max(w0, w1) * 1024 + (long long)(std::fabs(ms - prop) * 16);     // fewest waves, then closest to proportional
           if (best < 0 || w < best) { best = w; best_ms = ms; }
         }
-        g.die_tab = dm->tab; g.m_split = best_ms; g.die_pairs0 = dm->pairs[0]; g.die_pairs1 = dm->pairs[1];
+        // claim words of this launch: the next 128-word line of a 256-line ring (a line is reused 256 die-aware launches later)
+        unsigned* claim = die_next_claims(dm);
+        EVO_CUDA(cudaMemsetAsync(claim, 0, DieMap::CLAIM_WORDS * sizeof(unsigned), st));
+        g.die_tab = dm->tab; g.die_claim = claim; g.m_split = best_ms; g.die_pairs0 = dm->pairs[0]; g.die_pairs1 = dm->pairs[1];
+        g.die_collide = die_mode == 2;
       }
     }
     cfg.gridDim = dim3(pairs * 2);

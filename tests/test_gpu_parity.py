@@ -350,7 +350,7 @@ def test_gemm_all_epilogues(variant, M, N, K):
 
 
 def test_gemm_die_aware_walk_is_bit_identical(tmp_path, monkeypatch):
-    """EVO_B200_GEMM_DIE_RASTER=1: each die of the GPU takes its own share of the row-blocks (csrc/die_map.cu measures which SM is on
+    """Die-aware walk (the default; EVO_B200_GEMM_DIE_RASTER=0 is the plain walk): each die of the GPU takes its own share of the row-blocks (csrc/die_map.cu measures which SM is on
     which die).  Only the order in which tiles are visited changes: every epilogue must give the same bits as the default walk, on
     a shape with a ragged last row-block, more tiles than CTA pairs and both grouping directions."""
     dump = tmp_path / "die_map.txt"
@@ -367,13 +367,13 @@ def test_gemm_die_aware_walk_is_bit_identical(tmp_path, monkeypatch):
             else:
                 monkeypatch.setenv("EVO_B200_GEMM_RASTER_N", raster)
             outs = {}
-            for die in ("0", "1"):
+            for die in ("0", "1", "2"):           # 2: every pair asks for the same slot first, the claim words sort it out
                 monkeypatch.setenv("EVO_B200_GEMM_DIE_RASTER", die)
                 outs[die] = [G._gemm(a, w, M, N, K, _lib.EPI_NONE, 0), G._gemm(a, w, M, N, K, _lib.EPI_BIAS_RESID, 0, bias=bias, resid=resid),
                              G._gemm(a, w, M, N, K, _lib.EPI_GELU_GATE, 0, ldc=N // 2)]
-            for x, y in zip(outs["0"], outs["1"]):
+            for x, y, z in zip(outs["0"], outs["1"], outs["2"]):
                 assert not torch.isnan(y.float()).any()
-                assert torch.equal(x, y)
+                assert torch.equal(x, y) and torch.equal(x, z)
     monkeypatch.delenv("EVO_B200_GEMM_RASTER_N", raising=False)
     text = dump.read_text() if dump.exists() else ""
     if not text.startswith("# ok"):
