@@ -349,12 +349,10 @@ def test_gemm_all_epilogues(variant, M, N, K):
     assert (out == ref).float().mean() > (0.97 if K <= 1024 else 0.88)
 
 
-def test_gemm_die_aware_walk_is_bit_identical(tmp_path, monkeypatch):
+def test_gemm_die_aware_walk_is_bit_identical(monkeypatch):
     """Die-aware walk (the default; EVO_B200_GEMM_DIE_RASTER=0 is the plain walk): each die of the GPU takes its own share of the row-blocks (csrc/die_map.cu measures which SM is on
     which die).  Only the order in which tiles are visited changes: every epilogue must give the same bits as the default walk, on
     a shape with a ragged last row-block, more tiles than CTA pairs and both grouping directions."""
-    dump = tmp_path / "die_map.txt"
-    monkeypatch.setenv("EVO_B200_GEMM_DIE_DUMP", str(dump))
     torch.manual_seed(5)
     for M, N, K in [(8200, 1024, 256), (16500, 512, 128), (9000, 2560, 64)]:
         a = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
@@ -375,11 +373,34 @@ def test_gemm_die_aware_walk_is_bit_identical(tmp_path, monkeypatch):
                 assert not torch.isnan(y.float()).any()
                 assert torch.equal(x, y) and torch.equal(x, z)
     monkeypatch.delenv("EVO_B200_GEMM_RASTER_N", raising=False)
+
+
+def test_die_map_calibration_in_a_fresh_process(tmp_path):
+    """The SM -> die map is measured once per device and process, at the first die-aware GEMM: run one in a fresh interpreter with
+    EVO_B200_GEMM_DIE_DUMP set and read what the calibration concluded.  A rejected calibration is legal (the GEMM then keeps the
+    plain walk) but worth seeing, so it skips with the reason; an accepted one must be a plausible two-die split with TPC-mates together."""
+    import subprocess
+    dump = tmp_path / "die_map.txt"
+    code = (
+        "import ctypes as C, torch\n"
+        "from evo_b200 import _lib\n"
+        "M, N, K = 8200, 1024, 256\n"
+        "a = torch.randn(M, K, device='cuda:0').bfloat16(); w = torch.randn(N, K, device='cuda:0').bfloat16(); out = torch.empty(M, N, dtype=torch.bfloat16, device='cuda:0')\n"
+        "p = _lib.GemmParams(A=a.data_ptr(), lda=K, W=w.data_ptr(), C=out.data_ptr(), ldc=N, bias=None, residual=None, ldr=N, M=M, N=N, K=K, epilogue=0, variant=0)\n"
+        "_lib.check(_lib.lib().evo_gemm(C.byref(p), C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'evo_gemm')\n"
+        "torch.cuda.synchronize()\n"
+        "ref = a.float() @ w.float().T\n"
+        "assert (out.float() - ref).abs().max().item() <= 0.02 * ref.abs().max().item()\n")
+    env = dict(os.environ, EVO_B200_GEMM_DIE_DUMP=str(dump), EVO_B200_GEMM_DIE_RASTER="1", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
     text = dump.read_text() if dump.exists() else ""
+    assert text, "the first die-aware GEMM of a process must calibrate (and dump when asked to)"
     if not text.startswith("# ok"):
-        pytest.skip("the SM -> die calibration was rejected on this GPU (%s): the die-aware walk stayed off" % (text.splitlines()[0] if text else "no dump"))
+        pytest.skip("the SM -> die calibration was rejected on this GPU (%s): the die-aware walk stays off" % text.splitlines()[0])
     dies = [int(line.split()[1]) for line in text.splitlines() if line and not line.startswith("#")]
     assert len(dies) == torch.cuda.get_device_properties(0).multi_processor_count and min(dies.count(0), dies.count(1)) >= len(dies) // 4
+    assert all(dies[2 * t] == dies[2 * t + 1] for t in range(len(dies) // 2))
 
 
 def test_gemm_tile_major_weights_variant3():
