@@ -22,6 +22,12 @@ at the 0.2.x tag) in plain PyTorch, anchored on the reference's call sites:
   evo/generation.py:152   logits, d = model(x, inference_params_dict=d)
   evo/generation.py:162   stripedhyena.sample.sample(...)
 
+What IS run from the reference itself: the host code around the model call.  tests/golden/
+make_reference_host_golden.py imports /root/reference/evo/{tokenizer,scoring,generation,models}.py,
+scripts/{score,generate}.py and semantic_design/semantic_design.py unmodified (a stand-in satisfies
+their `import stripedhyena`) and drives them with THIS model; tests/golden/reference_host.{json,npz}
+hold what they returned.  That pins evo_b200's host layer, not this file's arithmetic.
+
 The attention sub-path is restated from flash_attn (installed in the build
 container, v2.8.3): flash_attn/modules/mha.py:573-704 (MHA.forward),
 mha.py:230-279 (SelfAttention), layers/rotary.py:23-35 and :382-416.  That part

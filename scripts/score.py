@@ -13,6 +13,8 @@ in file order.  --random-init / --model-dir are for boxes without network.
 """
 import argparse
 
+import numpy as np
+
 from evo_b200 import Evo
 from evo_b200.frontend import read_fasta, score_many
 
@@ -41,8 +43,15 @@ def main(argv=None):
     with open(args.output_tsv, 'w') as f:
         f.write('seqs\tscores\n')
         for s, v in zip(seqs, scores):
-            f.write(f'{s}\t{v}\n')
+            f.write(f'{s}\t{_tsv_float(v)}\n')
     return scores
+
+
+def _tsv_float(v):
+    """The text pandas' to_csv writes for a float32 score column (the reference's scripts/score.py:57-58): the shortest decimal
+    that round-trips the float32, an empty field for NaN."""
+    v32 = np.float32(v)
+    return '' if np.isnan(v32) else str(v32)
 
 
 if __name__ == '__main__':

@@ -253,6 +253,114 @@ def checkpoint_cases(RM):
     return out
 
 
+def _load_reference_script(name):
+    """A file under /root/reference/scripts as a module of its own (the repo has a `scripts` package of the same name)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_scripts_" + name, os.path.join(REFERENCE, "scripts", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cli_cases(RT, RM):
+    """scripts/score.py and scripts/generate.py of the reference, main() run as written.  Stand-ins: Biopython is not installed, so
+    `Bio.SeqIO.parse` is a 10-line FASTA reader (what is pinned is everything AFTER the parse: batching in file order, the TSV
+    pandas writes, what is printed); `Evo(name)` returns the oracle model instead of downloading a checkpoint."""
+    import contextlib
+    import io
+
+    class Record:
+        def __init__(self, seq):
+            self.seq = seq
+
+    def parse(path, fmt):
+        assert fmt == "fasta"
+        cur = None
+        for line in open(path):
+            line = line.strip()
+            if line.startswith(">"):
+                if cur is not None:
+                    yield Record("".join(cur))
+                cur = []
+            elif line and cur is not None:
+                cur.append(line)
+        if cur is not None:
+            yield Record("".join(cur))
+
+    bio, seqio = types.ModuleType("Bio"), types.ModuleType("Bio.SeqIO")
+    seqio.parse = parse
+    bio.SeqIO = seqio
+    sys.modules["Bio"], sys.modules["Bio.SeqIO"] = bio, seqio
+    cfg, sd = tiny()
+    made = []
+
+    class ModelWithTo(OracleAsModel):
+        def to(self, device):
+            self.moved_to = str(device)
+            return self
+
+    class FakeEvo:
+        def __init__(self, model_name, device=None):
+            self.model, self.tokenizer = ModelWithTo(cfg, sd, torch.float64), RT.CharLevelTokenizer(512)
+            made.append([model_name, device])
+
+    out = {}
+    fasta = os.path.join(ROOT, "examples", "example_seqs.fasta")
+    score = _load_reference_script("score")
+    score.Evo = FakeEvo
+    with tempfile.TemporaryDirectory() as tmp:
+        tsv = os.path.join(tmp, "scores.tsv")
+        argv, buf = sys.argv, io.StringIO()
+        sys.argv = ["score.py", "--input-fasta", fasta, "--output-tsv", tsv, "--device", "cpu", "--batch-size", "2"]
+        try:
+            with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+                score.main()
+        finally:
+            sys.argv = argv
+        out["score"] = {"argv": ["--input-fasta", "examples/example_seqs.fasta", "--output-tsv", "<tsv>", "--device", "cpu", "--batch-size", "2"],
+                        "tsv": open(tsv).read(), "stdout": buf.getvalue(), "evo_args": made[-1]}
+    gen = _load_reference_script("generate")
+    gen.Evo = FakeEvo
+    argv, buf = sys.argv, io.StringIO()
+    sys.argv = ["generate.py", "--prompt", "ACGTAC", "--n-samples", "2", "--n-tokens", "6", "--top-k", "1", "--device", "cpu"]
+    try:
+        with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+            gen.main()
+    finally:
+        sys.argv = argv
+    out["generate"] = {"argv": sys.argv and ["--prompt", "ACGTAC", "--n-samples", "2", "--n-tokens", "6", "--top-k", "1", "--device", "cpu"], "stdout": buf.getvalue(), "evo_args": made[-1]}
+    return out
+
+
+PROMPT_CSV = "\ufeffSequence,Note\r\nACGTACGT,a\r\nTTGA,b\r\nGGGGCCCC,c\r\nAC,d\r\nTTTTAAAA,e\r\nCCCC,f\r\nACGTACGA,g\r\nAAAATTTT,h\r\n\"ACGT,ACGT\",quoted\r\n"
+
+
+def bucketing_cases():
+    """semantic_design/semantic_design.py:read_prompts (:39-100), imported with the rest of its module (Biopython stand-ins for the
+    names the module imports at the top; read_prompts itself uses csv only)."""
+    bio = sys.modules.get("Bio") or types.ModuleType("Bio")
+    for sub, names in (("SeqIO", ()), ("AlignIO", ()), ("Seq", ("Seq",)), ("SeqRecord", ("SeqRecord",))):
+        mod = sys.modules.get("Bio." + sub) or types.ModuleType("Bio." + sub)
+        for n in names:
+            setattr(mod, n, type(n, (), {}))
+        sys.modules["Bio." + sub] = mod
+        setattr(bio, sub, mod)
+    sys.modules["Bio"] = bio
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_semantic_design", os.path.join(REFERENCE, "semantic_design", "semantic_design.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {"csv": PROMPT_CSV}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "prompts.csv")
+        with open(path, "w", encoding="utf-8", newline="") as f:
+            f.write(PROMPT_CSV)
+        out["unbatched"] = mod.read_prompts(path, batched=False)
+        for bs in (150, 2, 1):
+            out[f"batched_{bs}"] = mod.read_prompts(path, batched=True, batch_size=bs)
+    return out
+
+
 def main():
     if not os.path.isdir(os.path.join(REFERENCE, "evo")):
         raise SystemExit("needs /root/reference (build container only)")
@@ -274,6 +382,8 @@ def main():
     doc["scoring"] = scoring_cases(RS, RT, arrays)
     doc["generation"] = generation_cases(RG, RS, RT, arrays)
     doc["checkpoint"] = checkpoint_cases(RM)
+    doc["cli"] = cli_cases(RT, RM)
+    doc["bucketing"] = bucketing_cases()
     with open(os.path.join(HERE, "reference_host.json"), "w") as f:
         json.dump(doc, f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "reference_host.npz"), **arrays)

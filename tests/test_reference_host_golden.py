@@ -226,3 +226,53 @@ def test_checkpoint_ingest_matches_the_reference(ref, tmp_path, monkeypatch):
     with pytest.raises(FileNotFoundError) as ex:
         load_checkpoint("evo-1-8k-base", config_path=str(cfg_path), streaming=False)
     assert str(ex.value).replace(str(empty), "<dir>") == want["no_files"]
+
+
+class _FakeEvo:
+    """Evo(...) without a checkpoint: the fixture's oracle model behind the scripts' `Evo` name."""
+    made = []
+
+    def __init__(self, model_name, device=None, **kw):
+        class Model(OracleAsModel):
+            def to(self, device):
+                return self
+        self.model, self.tokenizer = Model(), CharLevelTokenizer(512)
+        _FakeEvo.made.append([model_name, device])
+
+
+def test_score_cli_writes_the_reference_tsv(ref, tmp_path, monkeypatch, capsys):
+    """scripts/score.py main(): same file-order rows, same header, same float text as the pandas TSV of the reference's script."""
+    import scripts.score as cli
+    want = ref[0]["cli"]["score"]
+    monkeypatch.setattr(cli, "Evo", _FakeEvo)
+    tsv = tmp_path / "scores.tsv"
+    argv = [a if a != "<tsv>" else str(tsv) for a in want["argv"]]
+    argv[argv.index("examples/example_seqs.fasta")] = os.path.join(ROOT, "examples", "example_seqs.fasta")
+    cli.main(argv)
+    assert tsv.read_text() == want["tsv"]
+    assert capsys.readouterr().out == want["stdout"]
+    assert _FakeEvo.made[-1][0] == want["evo_args"][0]                           # default model name
+
+
+def test_generate_cli_prints_what_the_reference_prints(ref, monkeypatch, capsys):
+    import scripts.generate as cli
+    want = ref[0]["cli"]["generate"]
+    monkeypatch.setattr(cli, "Evo", _FakeEvo)
+    cli.main(want["argv"])
+    assert capsys.readouterr().out == want["stdout"]
+    assert _FakeEvo.made[-1][0] == want["evo_args"][0]
+
+
+def test_length_buckets_match_the_reference_read_prompts(ref, tmp_path):
+    """frontend.read_prompts_csv + length_buckets(mode="exact") = semantic_design.read_prompts (BOM, header row, quoted field,
+    first-seen order of the lengths, batches of <= batch_size identical-length prompts)."""
+    from evo_b200.frontend import length_buckets, read_prompts_csv
+    want = ref[0]["bucketing"]
+    path = tmp_path / "prompts.csv"
+    with open(path, "w", encoding="utf-8", newline="") as f:
+        f.write(want["csv"])
+    seqs = read_prompts_csv(str(path))
+    assert seqs == want["unbatched"]
+    for bs in (150, 2, 1):
+        got = [[seqs[i] for i in idx] for idx in length_buckets(seqs, batch_size=bs, mode="exact")]
+        assert got == want[f"batched_{bs}"], bs
