@@ -8,7 +8,10 @@
    model (Hyena, attention, Hyena).  stripedhyena itself is not importable here (SURVEY.md
    section 0.1), so this fixture guards the oracle against regressions; it does not pin it.
 
-    python tests/golden/make_golden.py
+3. kvcache_sampling_flash_attn.npz -- flash_attn's _update_kv_cache, CrossAttention(causal=True) and utils.generation.sample
+   run on CPU (see kvcache_and_sampling_fixture).
+
+    python tests/golden/make_golden.py [attention] [tiny_model] [kvcache_sampling]
 """
 import os
 import sys
@@ -65,8 +68,60 @@ def tiny_model_fixture():
                         fir0=d["hyena"].fir_state_dict[0].to(torch.float32).numpy())
 
 
+def kvcache_and_sampling_fixture():
+    """3. kvcache_sampling_flash_attn.npz -- more of flash_attn's OWN torch code, run on CPU:
+       * _update_kv_cache (modules/mha.py:338-367) with flash_attn.utils.generation.InferenceParams: a prefill of 5 tokens, then
+         two single-token appends at seqlen_offset 5 and 6 into a (max_batch 3, max_seqlen 16) cache, batch 2;
+       * CrossAttention(causal=True) (mha.py:280-335) on (q of the new tokens, kv = cache[:, :offset + Lq]): the decode / continued
+         prefill attention MHA.forward takes when use_flash_attn is False (mha.py:502-540, 689-700) -- bottom-right aligned mask;
+       * utils/generation.sample (generation.py:70-98), the code stripedhyena/sample.py copies: picks for seeded draws over
+         top-k / top-p / temperature settings on fp32 logits."""
+    from flash_attn.modules.mha import CrossAttention, _update_kv_cache
+    from flash_attn.utils.generation import InferenceParams, sample
+
+    torch.manual_seed(4321)
+    B, H, d = 2, 2, 128
+    out = {}
+    ip = InferenceParams(max_seqlen=16, max_batch_size=3)
+    attn = CrossAttention(causal=True)
+    steps = [(0, 5), (5, 1), (6, 1), (7, 3)]            # (seqlen_offset, new tokens): prefill, two decode steps, a continued prefill
+    for n, (off, L) in enumerate(steps):
+        q = torch.randn(B, L, H, d, dtype=torch.float32)
+        kv = torch.randn(B, L, 2, H, d, dtype=torch.float32)
+        ip.seqlen_offset = off
+        fresh = 7 not in ip.key_value_memory_dict
+        seen = _update_kv_cache(kv, ip, 7)
+        if fresh:       # torch.empty in the reference: give the never-written part a value so the fixture is reproducible
+            cache = ip.key_value_memory_dict[7]
+            cache[B:] = 0
+            cache[:, L:] = 0
+        assert tuple(seen.shape) == (B, off + L, 2, H, d)
+        ctx = attn(q, seen)
+        out[f"q_{n}"], out[f"kv_{n}"], out[f"ctx_{n}"] = q.numpy(), kv.numpy(), ctx.numpy()
+    out["cache_final"] = ip.key_value_memory_dict[7].numpy().copy()
+    out["steps"] = np.array(steps)
+    # sampling
+    g = torch.Generator().manual_seed(99)
+    logits = torch.randn(6, 512, generator=g) * 2.5
+    out["sample_logits"] = logits.numpy()
+    cases = [(1, 0.0, 1.0), (4, 0.0, 1.0), (4, 1.0, 0.7), (50, 0.7, 1.0), (50, 0.7, 0.5), (0, 0.9, 1.0), (0, 0.0, 1.3), (600, 0.5, 1.0)]
+    out["sample_cases"] = np.array(cases, dtype=np.float64)
+    for n, (k, p, t) in enumerate(cases):
+        picks = []
+        for seed in range(8):
+            torch.manual_seed(1000 + seed)
+            picks.append(sample(logits.clone(), top_k=k, top_p=p, temperature=t).numpy())
+        out[f"sample_picks_{n}"] = np.stack(picks)
+    np.savez_compressed(os.path.join(HERE, "kvcache_sampling_flash_attn.npz"), **out)
+
+
 if __name__ == "__main__":
-    attention_fixture()
-    tiny_model_fixture()
+    which = sys.argv[1:] or ["attention", "tiny_model", "kvcache_sampling"]
+    if "attention" in which:
+        attention_fixture()
+    if "tiny_model" in which:
+        tiny_model_fixture()
+    if "kvcache_sampling" in which:
+        kvcache_and_sampling_fixture()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -77,3 +77,22 @@ def test_gpu_entropies_land_on_the_reference_scoring_code_output(ref):
     diffs = np.concatenate([np.abs(np.asarray(e, dtype=np.float64) - arr[f"entropy_fp64_{k}"]) for k, e in enumerate(ent)])
     # entropies here span 0.5 .. 4.5 nats; the reference's bf16 pipeline (restated on CPU) is 0.021 mean / 0.082 max from exact arithmetic
     assert diffs.mean() < 0.1 and diffs.max() < 0.4, (diffs.mean(), diffs.max())
+
+
+def test_gpu_kv_append_replays_flash_attn_update_kv_cache(golden_dir):
+    """evo_kv_append against flash_attn's own _update_kv_cache (modules/mha.py:338-367, run on CPU for
+    tests/golden/kvcache_sampling_flash_attn.npz): a 5-token prefill, two single-token appends and a 3-token continuation into a
+    (3, 16) cache at batch 2 must leave the same cache (a copy: bit-exact on the bf16-rounded inputs)."""
+    import ctypes as C
+    g = np.load(os.path.join(golden_dir, "kvcache_sampling_flash_attn.npz"))
+    lib = _lib.lib()
+    H, d = g["q_0"].shape[2], g["q_0"].shape[3]
+    cache = torch.zeros(3, 16, 2, H, d, dtype=torch.bfloat16, device=DEV)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for n, (off, L) in enumerate(g["steps"]):
+        off, L = int(off), int(L)
+        kv = torch.from_numpy(g[f"kv_{n}"]).bfloat16()                     # (B, L, 2, H, d)
+        qkv = torch.cat([torch.from_numpy(g[f"q_{n}"]).bfloat16()[:, :, None], kv], dim=2).contiguous().to(DEV)     # (B, L, 3, H, d)
+        _lib.check(lib.evo_kv_append(_lib.ptr(qkv), _lib.ptr(cache), qkv.shape[0], L, H, d, off, 16, stream), "evo_kv_append")
+    torch.cuda.synchronize()
+    assert torch.equal(cache.cpu(), torch.from_numpy(g["cache_final"]).bfloat16())

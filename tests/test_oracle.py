@@ -163,3 +163,37 @@ def test_sample_greedy_and_topk():
     s = O.sample(lg.clone(), top_k=4, top_p=0.9, temperature=0.7)
     top4 = lg.topk(4, dim=-1).indices
     assert all(s[i] in top4[i] for i in range(5))
+
+
+@pytest.fixture(scope="module")
+def kvs(golden_dir):
+    return np.load(os.path.join(golden_dir, "kvcache_sampling_flash_attn.npz"))
+
+
+def test_cache_form_attention_matches_flash_attn(kvs):
+    """Decode / continued-prefill attention: flash_attn's _update_kv_cache + CrossAttention(causal=True) (modules/mha.py:280-367,
+    run on CPU for the fixture) vs the oracle's cache write (attention_block) and causal_attention(q, k, v, q_offset)."""
+    steps = [tuple(int(v) for v in row) for row in kvs["steps"]]
+    B, H, d = kvs["q_0"].shape[0], kvs["q_0"].shape[2], kvs["q_0"].shape[3]
+    cache = torch.zeros(3, 16, 2, H, d)
+    for n, (off, L) in enumerate(steps):
+        q, kv = torch.from_numpy(kvs[f"q_{n}"]), torch.from_numpy(kvs[f"kv_{n}"])
+        cache[:B, off:off + L, 0] = kv[:, :, 0]                  # the oracle's cache write (attention_block), statement for statement
+        cache[:B, off:off + L, 1] = kv[:, :, 1]
+        ctx = O.causal_attention(q, cache[:B, :off + L, 0], cache[:B, :off + L, 1], q_offset=off)
+        np.testing.assert_allclose(ctx.numpy(), kvs[f"ctx_{n}"], rtol=0, atol=3e-6)
+    np.testing.assert_array_equal(cache.numpy(), kvs["cache_final"])
+
+
+def test_samplers_match_flash_attn_sample(kvs):
+    """flash_attn.utils.generation.sample (the code stripedhyena/sample.py copies; run on CPU for the fixture) vs the oracle's
+    sample and evo_b200's host sampler: the same picks for the same torch seed, over greedy / top-k / top-p / temperature /
+    full-vocabulary settings on fp32 logits."""
+    from evo_b200.stripedhyena.sample import sample as product_sample
+    logits = torch.from_numpy(kvs["sample_logits"])
+    for n, (k, p, t) in enumerate(kvs["sample_cases"]):
+        for fn in (O.sample, product_sample):
+            for seed in range(8):
+                torch.manual_seed(1000 + seed)
+                got = fn(logits.clone(), top_k=int(k), top_p=float(p), temperature=float(t))
+                np.testing.assert_array_equal(got.numpy(), kvs[f"sample_picks_{n}"][seed], err_msg=f"{fn.__module__} case {n} seed {seed}")
