@@ -32,7 +32,9 @@ The attention sub-path is restated from flash_attn (installed in the build
 container, v2.8.3): flash_attn/modules/mha.py:573-704 (MHA.forward),
 mha.py:230-279 (SelfAttention), layers/rotary.py:23-35 and :382-416.  That part
 IS pinned: tests/golden/make_golden.py imports flash_attn's own torch code paths
-and the fixtures under tests/golden/ hold its outputs (tests/test_oracle.py).
+and the fixtures under tests/golden/ hold its outputs (tests/test_oracle.py): rotary
+tables and application, SelfAttention, _update_kv_cache, CrossAttention in cache form,
+utils.generation.sample, and MHA.forward as a whole (stateless, prefill, steps).
 
 Two arithmetic modes:
   dtype=torch.bfloat16  "faithful": every op runs in the dtype the reference runs

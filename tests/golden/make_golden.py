@@ -10,8 +10,10 @@
 
 3. kvcache_sampling_flash_attn.npz -- flash_attn's _update_kv_cache, CrossAttention(causal=True) and utils.generation.sample
    run on CPU (see kvcache_and_sampling_fixture).
+4. mha_flash_attn.npz -- flash_attn's whole MHA.forward on CPU (stateless, prefill + steps) with the Triton rotary call replaced
+   by flash_attn's own torch statement of it (see mha_block_fixture).
 
-    python tests/golden/make_golden.py [attention] [tiny_model] [kvcache_sampling]
+    python tests/golden/make_golden.py [attention] [tiny_model] [kvcache_sampling] [mha]
 """
 import os
 import sys
@@ -115,8 +117,58 @@ def kvcache_and_sampling_fixture():
     np.savez_compressed(os.path.join(HERE, "kvcache_sampling_flash_attn.npz"), **out)
 
 
+def mha_block_fixture():
+    """4. mha_flash_attn.npz -- flash_attn's MHA.forward itself (modules/mha.py:573-704) on CPU, fp32, configured as StripedHyena's
+    AttentionBlock configures it (causal, qkv and out-proj bias, rotary over the full head_dim 128, use_flash_attn=False -- the
+    torch SelfAttention / CrossAttention branch): stateless over 8 tokens; then with flash_attn's InferenceParams a 6-token
+    prefill and two single-token steps (rotary at seqlen_offset with the table built to max_seqlen, _update_kv_cache,
+    cache-form attention).  ONE patch, the one SURVEY.md 8c names: RotaryEmbedding.forward ends in a Triton kernel that cannot run
+    on CPU, so `apply_rotary_emb_qkv_` is replaced by flash_attn's own torch statement of it (apply_rotary_emb_torch on q and k at
+    cos/sin[offset : offset + L]); everything else -- Wqkv, the `(three h d)` split, the cos/sin cache, the cache write, the masks,
+    out_proj -- is flash_attn's code as installed."""
+    import flash_attn.layers.rotary as R
+    from flash_attn.modules.mha import MHA
+    from flash_attn.utils.generation import InferenceParams
+
+    def qkv_rotary_torch(qkv, cos, sin, cos_k=None, sin_k=None, interleaved=False, seqlen_offsets=0, num_heads_q=None):
+        assert cos_k is None and sin_k is None and isinstance(seqlen_offsets, int) and num_heads_q is None
+        L = qkv.shape[1]
+        c, s_ = cos[seqlen_offsets:seqlen_offsets + L], sin[seqlen_offsets:seqlen_offsets + L]
+        q = R.apply_rotary_emb_torch(qkv[:, :, 0], c, s_, interleaved)
+        k = R.apply_rotary_emb_torch(qkv[:, :, 1], c, s_, interleaved)
+        return torch.stack([q, k, qkv[:, :, 2]], dim=2)
+
+    real = R.apply_rotary_emb_qkv_
+    R.apply_rotary_emb_qkv_ = qkv_rotary_torch
+    try:
+        torch.manual_seed(777)
+        D, H, B = 256, 2, 2
+        mha = MHA(D, H, qkv_proj_bias=True, out_proj_bias=True, causal=True, layer_idx=1, rotary_emb_dim=D // H, use_flash_attn=False)
+        with torch.no_grad():
+            mha.Wqkv.bias.normal_(0, 0.1)
+            mha.out_proj.bias.normal_(0, 0.1)
+        x = torch.randn(B, 8, D)
+        out = {"x": x.numpy(), "Wqkv_w": mha.Wqkv.weight.detach().numpy(), "Wqkv_b": mha.Wqkv.bias.detach().numpy(),
+               "out_w": mha.out_proj.weight.detach().numpy(), "out_b": mha.out_proj.bias.detach().numpy(), "inv_freq": mha.rotary_emb.inv_freq.numpy()}
+        with torch.no_grad():
+            out["y_stateless"] = mha(x).numpy()
+            ip = InferenceParams(max_seqlen=32, max_batch_size=B)
+            out["y_prefill"] = mha(x[:, :6], inference_params=ip).numpy()
+            ip.key_value_memory_dict[1][:, 6:] = 0           # torch.empty in flash_attn: pin the never-written rows
+            ip.seqlen_offset = 6
+            out["y_step6"] = mha(x[:, 6:7], inference_params=ip).numpy()
+            ip.seqlen_offset = 7
+            out["y_step7"] = mha(x[:, 7:8], inference_params=ip).numpy()
+            out["cache"] = ip.key_value_memory_dict[1].numpy().copy()
+    finally:
+        R.apply_rotary_emb_qkv_ = real
+    np.savez_compressed(os.path.join(HERE, "mha_flash_attn.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["attention", "tiny_model", "kvcache_sampling"]
+    which = sys.argv[1:] or ["attention", "tiny_model", "kvcache_sampling", "mha"]
+    if "mha" in which:
+        mha_block_fixture()
     if "attention" in which:
         attention_fixture()
     if "tiny_model" in which:

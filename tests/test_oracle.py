@@ -197,3 +197,33 @@ def test_samplers_match_flash_attn_sample(kvs):
                 torch.manual_seed(1000 + seed)
                 got = fn(logits.clone(), top_k=int(k), top_p=float(p), temperature=float(t))
                 np.testing.assert_array_equal(got.numpy(), kvs[f"sample_picks_{n}"][seed], err_msg=f"{fn.__module__} case {n} seed {seed}")
+
+
+def test_attention_block_matches_flash_attn_mha_forward(golden_dir, monkeypatch):
+    """The oracle's attention_block -- Wqkv, `(three h d)` split, rotary at seqlen_offset, cache write, cache-form causal attention,
+    out_proj -- against flash_attn's MHA.forward run on CPU (tests/golden/make_golden.py: mha_block_fixture; the Triton rotary call
+    is the one patched statement).  Pre-norm and the MLP half of the block are stripedhyena's, not flash_attn's: they are switched
+    to identities here so that attention_block(u) - u is exactly what MHA.forward returns."""
+    g = np.load(os.path.join(golden_dir, "mha_flash_attn.npz"))
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    cfg["max_seqlen"] = 32
+    sd = {k: v.float() for k, v in O.random_state_dict(cfg, seed=1).items()}
+    p = "blocks.1.inner_mha_cls."
+    sd[p + "Wqkv.weight"], sd[p + "Wqkv.bias"] = torch.from_numpy(g["Wqkv_w"]), torch.from_numpy(g["Wqkv_b"])
+    sd[p + "out_proj.weight"], sd[p + "out_proj.bias"] = torch.from_numpy(g["out_w"]), torch.from_numpy(g["out_b"])
+    m = O.OracleStripedHyena(cfg, sd, torch.float32)
+    monkeypatch.setattr(O, "rms_norm", lambda x, scale, eps: x)
+    monkeypatch.setattr(m, "_mlp_res", lambda prefix, a: a)
+    np.testing.assert_array_equal(O.rotary_tables(4, 128, dtype=torch.float32)[0].numpy(),
+                                  torch.cos(torch.outer(torch.arange(4, dtype=torch.float32), torch.from_numpy(g["inv_freq"]))).numpy())
+    x = torch.from_numpy(g["x"])
+    np.testing.assert_allclose((m.attention_block(1, x) - x).numpy(), g["y_stateless"], rtol=0, atol=2e-5)
+    ip = m.initialize_inference_params()["mha"]
+    ip.max_batch_size = 2
+    np.testing.assert_allclose((m.attention_block(1, x[:, :6], ip) - x[:, :6]).numpy(), g["y_prefill"], rtol=0, atol=2e-5)
+    for t in (6, 7):
+        ip.seqlen_offset = t
+        np.testing.assert_allclose((m.attention_block(1, x[:, t:t + 1], ip) - x[:, t:t + 1]).numpy(), g[f"y_step{t}"], rtol=0, atol=2e-5)
+    cache = ip.key_value_memory_dict[1]
+    assert tuple(cache.shape) == tuple(g["cache"].shape)                    # (max_batch_size, max_seqlen, 2, H, head_dim): mha.py:344-353
+    np.testing.assert_allclose(cache.numpy(), g["cache"], rtol=0, atol=2e-6)
