@@ -96,3 +96,58 @@ def test_gpu_kv_append_replays_flash_attn_update_kv_cache(golden_dir):
         _lib.check(lib.evo_kv_append(_lib.ptr(qkv), _lib.ptr(cache), qkv.shape[0], L, H, d, off, 16, stream), "evo_kv_append")
     torch.cuda.synchronize()
     assert torch.equal(cache.cpu(), torch.from_numpy(g["cache_final"]).bfloat16())
+
+
+def test_gpu_attention_layer_through_the_c_abi_lands_on_flash_attn_mha_forward(golden_dir):
+    """The product's attention layer -- evo_rope_tables, evo_gemm with the bias + rotary epilogue (Wqkv), evo_attn_fwd_ws (the
+    default variant), evo_kv_append, evo_gemm with the bias epilogue (out_proj) -- against flash_attn's MHA.forward run on CPU in
+    fp32 (tests/golden/mha_flash_attn.npz, made by make_golden.py: mha_block_fixture): the stateless forward over 8 tokens, and
+    token 6 as a single-token step over a cache holding the 6-token prefill.  Tolerance: the bf16 pipeline restated on CPU is
+    3.8e-3 max / 6.5e-4 mean from these fp32 numbers (outputs up to 1.06); the GPU gets 0.02 / 0.004."""
+    import ctypes as C
+    import math
+    sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
+    import gpu_bringup as G
+    from evo_b200.stripedhyena import model as M_
+    G._imports()
+    g = np.load(os.path.join(golden_dir, "mha_flash_attn.npz"))
+    lib = _lib.lib()
+    stream = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    B, L, D, H, hd = 2, 8, 256, 2, 128
+    dev = lambda name: torch.from_numpy(g[name]).bfloat16().to(DEV).contiguous()
+    x, wqkv, bqkv, wo, bo = dev("x"), dev("Wqkv_w"), dev("Wqkv_b"), dev("out_w"), dev("out_b")
+    inv_freq = torch.from_numpy(g["inv_freq"]).float().to(DEV).contiguous()
+    cos = torch.empty(32, hd // 2, dtype=torch.bfloat16, device=DEV)
+    sin = torch.empty_like(cos)
+    _lib.check(lib.evo_rope_tables(_lib.ptr(cos), _lib.ptr(sin), _lib.ptr(inv_freq), 0, 32, hd // 2, 1.0, stream()), "evo_rope_tables")
+
+    def wqkv_rope(rows, n_seq, n_tok, off):
+        out = torch.full((n_seq * n_tok, 3 * D), float("nan"), dtype=torch.bfloat16, device=DEV)
+        p = _lib.GemmParams(A=rows.data_ptr(), lda=D, W=wqkv.data_ptr(), C=out.data_ptr(), ldc=3 * D, bias=bqkv.data_ptr(), residual=None, ldr=3 * D,
+                            M=n_seq * n_tok, N=3 * D, K=D, epilogue=_lib.EPI_BIAS_ROPE, variant=0,
+                            rope_cos=cos.data_ptr() + off * (hd // 2) * 2, rope_sin=sin.data_ptr() + off * (hd // 2) * 2, rope_L=n_tok, rope_cols=2 * D)
+        _lib.check(lib.evo_gemm(C.byref(p), stream()), "evo_gemm(rope)")
+        return out
+
+    def close(got, want):
+        err = (got.float().cpu() - torch.from_numpy(want).reshape(got.shape)).abs()
+        assert torch.isfinite(got.float()).all() and err.max().item() < 0.02 and err.mean().item() < 0.004, (err.max().item(), err.mean().item())
+
+    # stateless: MHA.forward(x)
+    qkv = wqkv_rope(x.view(B * L, D), B, L, 0)
+    ctx = G._attn(qkv, B, L, H, M_.ATTN_VARIANT)
+    y = G._gemm(ctx.view(B * L, D), wo, B * L, D, D, _lib.EPI_BIAS, 0, bias=bo)
+    close(y.view(B, L, D), g["y_stateless"])
+    # prefill of 6 tokens into a (2, 32) cache, then token 6 as one step at seqlen_offset 6 (mha.py:344-367, 502-540)
+    cache = torch.zeros(B, 32, 2, H, hd, dtype=torch.bfloat16, device=DEV)
+    pre = wqkv_rope(x[:, :6].contiguous().view(B * 6, D), B, 6, 0)
+    _lib.check(lib.evo_kv_append(_lib.ptr(pre), _lib.ptr(cache), B, 6, H, hd, 0, 32, stream()), "evo_kv_append")
+    y_pre = G._gemm(G._attn(pre, B, 6, H, M_.ATTN_VARIANT, cache=cache, off=0).view(B * 6, D), wo, B * 6, D, D, _lib.EPI_BIAS, 0, bias=bo)
+    close(y_pre.view(B, 6, D), g["y_prefill"])
+    step = wqkv_rope(x[:, 6:7].contiguous().view(B, D), B, 1, 6)
+    _lib.check(lib.evo_kv_append(_lib.ptr(step), _lib.ptr(cache), B, 1, H, hd, 6, 32, stream()), "evo_kv_append")
+    y6 = G._gemm(G._attn(step, B, 1, H, M_.ATTN_VARIANT, cache=cache, off=6).view(B, D), wo, B, D, D, _lib.EPI_BIAS, 0, bias=bo)
+    close(y6.view(B, 1, D), g["y_step6"])
+    want_cache = torch.from_numpy(g["cache"])[:, :7]
+    err = (cache[:, :7].float().cpu() - want_cache).abs()
+    assert err.max().item() < 0.03 * max(1.0, want_cache.abs().max().item())        # rotary'd k / projected v, bf16 vs fp32
