@@ -162,6 +162,12 @@ def load_streaming(model, model_dir: str, device) -> Dict[str, int]:
     if "embedding_layer.weight" in seen or "unembed.weight" in seen:                         # tied embeddings: either name fills both
         if targets.get("unembed.weight", (None,))[0] is targets.get("embedding_layer.weight", (1,))[0]:
             seen.update(("embedding_layer.weight", "unembed.weight"))
+    if "unembed.weight" in targets and "unembed.weight" not in seen and "embedding_layer.weight" in seen:
+        # untied model, checkpoint without unembed.weight: the reference fills it from the embedding whatever the config says
+        # (evo/models.py:133-137)
+        with torch.no_grad():
+            targets["unembed.weight"][0].data.copy_(targets["embedding_layer.weight"][0].data)
+        seen.add("unembed.weight")
     missing = [k for k in targets if k not in seen]
     if missing or unexpected or errors:
         msg = [f"Error(s) in loading state_dict for {type(model).__name__}:"]

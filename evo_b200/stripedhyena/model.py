@@ -704,8 +704,12 @@ class StripedHyena(nn.Module):
                       "step": torch.zeros(1, dtype=torch.int64, device=dev), "lp": torch.zeros(C.sizeof(_lib.LoopParams), dtype=torch.uint8, device=dev),
                       "lp_host": torch.zeros(C.sizeof(_lib.LoopParams), dtype=torch.uint8).pin_memory()}
                 self._loop = st
+            if st.get("lp_copied") is not None:
+                st["lp_copied"].synchronize()       # a previous call's async copy may not have left the pinned staging buffer yet
             C.memmove(st["lp_host"].data_ptr(), C.addressof(lp), C.sizeof(lp))
             st["lp"].copy_(st["lp_host"], non_blocking=True)
+            st["lp_copied"] = torch.cuda.Event()
+            st["lp_copied"].record()
             st["pos"].fill_(int(start_pos))
             st["step"].zero_()
             st["x"].copy_(x.to(torch.long))

@@ -385,6 +385,24 @@ def test_streaming_ingest_equals_host_state_dict_path(tmp_path):
             load_checkpoint("evo-1-8k-base", config_path=cfg_path, model_dir=str(bad))
 
 
+def test_untied_model_without_unembed_in_the_checkpoint_is_filled_from_the_embedding(tmp_path):
+    """evo/models.py:133-137 copies embedding_layer.weight into a missing unembed.weight whatever tie_embeddings says; both ingest
+    paths must do the same (the Evo configs are tied, so this is the edge the reference's unconditional copy creates)."""
+    from safetensors.torch import save_file
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    cfg["tie_embeddings"] = False
+    sd = O.random_state_dict(cfg, seed=3)
+    sd.pop("unembed.weight")
+    save_file({"backbone." + k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "model.safetensors"))
+    (tmp_path / "c.yml").write_text(yaml.safe_dump(cfg))
+    a = load_checkpoint("evo-1-8k-base", config_path=str(tmp_path / "c.yml"), model_dir=str(tmp_path), streaming=True)
+    b = load_checkpoint("evo-1-8k-base", config_path=str(tmp_path / "c.yml"), model_dir=str(tmp_path), streaming=False)
+    assert a.unembed is not a.embedding_layer
+    sa, sb = a.state_dict(), b.state_dict()
+    assert set(sa) == set(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert torch.equal(sa["unembed.weight"], sa["embedding_layer.weight"])
+
+
 def test_mlp_parameters_live_only_in_the_packed_layouts():
     """No second copy of the MLP weights: the module owns w12 / w3, the reference's key names exist at the state-dict boundary only."""
     cfg = O.tiny_config(num_layers=1, attn_layer_idxs=(), hidden_size=256, num_heads=2)
