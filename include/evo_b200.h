@@ -10,8 +10,8 @@
  *
  * Conventions
  *   - every pointer is a raw DEVICE pointer owned by the caller (a torch tensor);
- *     the library never allocates device memory except a small per-device cache
- *     (TMA descriptors / cuBLASLt handle for the test comparator);
+ *     the library never allocates device memory except one small per-device cache
+ *     (the SM -> die table and claim words of the GEMM's die-aware tile walk, csrc/die_map.cu);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
  *   - bf16 tensors are row-major with the innermost dimension contiguous;
  *   - return value 0 = ok, negative = error; evo_last_error() has the message;
