@@ -168,6 +168,12 @@ def load_streaming(model, model_dir: str, device) -> Dict[str, int]:
         with torch.no_grad():
             targets["unembed.weight"][0].data.copy_(targets["embedding_layer.weight"][0].data)
         seen.add("unembed.weight")
+    for key in [k for k in targets if k.endswith("rotary_emb.inv_freq") and k not in seen]:
+        # optional in a checkpoint (see stripedhyena.model._Rotary): absent -> the analytic value the constructor would hold
+        rot = model.get_submodule(key.rsplit(".", 1)[0])
+        with torch.no_grad():
+            targets[key][0].data.copy_(rot.analytic(device))
+        seen.add(key)
     missing = [k for k in targets if k not in seen]
     if missing or unexpected or errors:
         msg = [f"Error(s) in loading state_dict for {type(model).__name__}:"]

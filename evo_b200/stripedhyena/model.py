@@ -140,9 +140,23 @@ class _HyenaFilter(nn.Module):
 
 
 class _Rotary(nn.Module):
+    """Carrier of `inv_freq`.  flash_attn registers it as a NON-persistent buffer (layers/rotary.py:366); stripedhyena re-registers it
+    as a persistent one, so its checkpoints carry `...rotary_emb.inv_freq`.  That second fact is recalled, not verified here (SURVEY.md
+    A.7), so loading accepts both: a checkpoint value is used when present, the constructor's analytic value when absent -- what the
+    reference ends up with in either world."""
+
     def __init__(self, head_dim, base):
         super().__init__()
-        self.register_buffer("inv_freq", 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim)))
+        self.head_dim, self.base = head_dim, base
+        self.register_buffer("inv_freq", self.analytic())
+
+    def analytic(self, device=None):
+        return 1.0 / (self.base ** (torch.arange(0, self.head_dim, 2, dtype=torch.float32, device=device) / self.head_dim))
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        if prefix + "inv_freq" not in state_dict:
+            state_dict = {**state_dict, prefix + "inv_freq": self.inv_freq if self.inv_freq.device.type != "meta" else self.analytic()}
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
 
 class _MHA(nn.Module):

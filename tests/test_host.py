@@ -403,6 +403,34 @@ def test_untied_model_without_unembed_in_the_checkpoint_is_filled_from_the_embed
     assert torch.equal(sa["unembed.weight"], sa["embedding_layer.weight"])
 
 
+def test_checkpoint_without_inv_freq_keys_loads_with_the_analytic_buffer(tmp_path):
+    """flash_attn registers rotary_emb.inv_freq as a non-persistent buffer; that stripedhyena re-registers it persistently (so that
+    the HF checkpoints carry it) is recalled, not verified.  Both ingest paths therefore accept a checkpoint with
+    or without those keys: present -> the checkpoint's values (see test_streaming_ingest...), absent -> the analytic table."""
+    from safetensors.torch import save_file
+    cfg = O.tiny_config(num_layers=2, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=3)
+    sd.pop("unembed.weight")
+    dropped = [k for k in sd if k.endswith("rotary_emb.inv_freq")]
+    assert dropped == ["blocks.1.inner_mha_cls.rotary_emb.inv_freq"]
+    for k in dropped:
+        sd.pop(k)
+    save_file({"backbone." + k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "model.safetensors"))
+    (tmp_path / "c.yml").write_text(yaml.safe_dump(cfg))
+    for streaming in (True, False):
+        m = load_checkpoint("evo-1-8k-base", config_path=str(tmp_path / "c.yml"), model_dir=str(tmp_path), streaming=streaming)
+        rot = m.blocks[1].inner_mha_cls.rotary_emb
+        want = 1.0 / (10000 ** (torch.arange(0, 128, 2, dtype=torch.float32) / 128))
+        assert rot.inv_freq.dtype == torch.float32 and torch.equal(rot.inv_freq, want)
+        assert "blocks.1.inner_mha_cls.rotary_emb.inv_freq" in m.state_dict()          # still exported under the reference's key
+    # any OTHER missing key is still a strict-mode error
+    sd.pop("blocks.1.inner_mha_cls.out_proj.bias")
+    save_file({"backbone." + k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "model.safetensors"))
+    for streaming in (True, False):
+        with pytest.raises(RuntimeError, match="Missing key"):
+            load_checkpoint("evo-1-8k-base", config_path=str(tmp_path / "c.yml"), model_dir=str(tmp_path), streaming=streaming)
+
+
 def test_mlp_parameters_live_only_in_the_packed_layouts():
     """No second copy of the MLP weights: the module owns w12 / w3, the reference's key names exist at the state-dict boundary only."""
     cfg = O.tiny_config(num_layers=1, attn_layer_idxs=(), hidden_size=256, num_heads=2)
