@@ -494,6 +494,26 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["e2e"] == {"value": d["value"], "unit": "nt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_bench_cpu_leg_switches_to_the_reference_package_when_it_is_importable(monkeypatch):
+    """bench.py's CPU legs (cpu_baseline, --impl reference) time the reference's own package instead of the oracle port whenever
+    `import stripedhyena` works (kind "reference"); absent -- everywhere so far -- they time the port.  Exercised with a stand-in
+    package and the geometry shrunk, so that the switch itself is tested, not the package."""
+    import importlib.util
+    from tests.test_oracle import _install_stand_in_package
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    tiny = O.tiny_config(num_layers=3, attn_layer_idxs=(1,), hidden_size=256, num_heads=2)
+    monkeypatch.setattr(O, "evo_config", lambda name="evo-1-8k-base": dict(tiny))
+    base, _, run = bench.cpu_baseline("evo-1-8k-base", target_seconds=0.3, threads=2)
+    assert base["kind"] == "port" and base["sample"].startswith("oracle (stripedhyena 0.2.2 restatement)")
+    _install_stand_in_package(monkeypatch)
+    base, _, run = bench.cpu_baseline("evo-1-8k-base", target_seconds=0.3, threads=2)
+    assert base["kind"] == "reference" and base["sample"].startswith("stripedhyena stand-in") and base["value"] > 0
+    assert run(32) > 0
+
+
 def test_bench_helpers_assemble_the_contract_fields():
     """bench.py's pure helpers: synthetic inputs are reproducible per seed, the roofline records carry the contract's keys and
     consistent arithmetic (achieved = work / time, frac = achieved / peak), and the workloads are the BASELINE.json configs."""

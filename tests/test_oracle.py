@@ -227,3 +227,68 @@ def test_attention_block_matches_flash_attn_mha_forward(golden_dir, monkeypatch)
     cache = ip.key_value_memory_dict[1]
     assert tuple(cache.shape) == tuple(g["cache"].shape)                    # (max_batch_size, max_seqlen, 2, H, head_dim): mha.py:344-353
     np.testing.assert_allclose(cache.numpy(), g["cache"], rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------ the real stripedhyena package (absent here; see oracle/real_reference.py)
+def _install_stand_in_package(monkeypatch):
+    """A `stripedhyena` package with the real one's interface, made of evo_b200's parameter tree (checkpoint key names, strict
+    loading, dtype policy) and the oracle's arithmetic: lets the bridge's plumbing run where the real package is absent."""
+    import sys
+    import types
+    from evo_b200.stripedhyena import StripedHyena as Tree, dotdict
+
+    class StandIn(Tree):
+        def _oracle(self):
+            return O.OracleStripedHyena(dict(self.config), dict(self.state_dict()), self.embedding_layer.weight.dtype)
+
+        def forward(self, x, inference_params_dict=None, padding_mask=None):
+            return self._oracle()(x, inference_params_dict)
+
+        def initialize_inference_params(self):
+            return self._oracle().initialize_inference_params()
+
+    pkg, model, utils = types.ModuleType("stripedhyena"), types.ModuleType("stripedhyena.model"), types.ModuleType("stripedhyena.utils")
+    pkg.__path__, pkg.__version__ = [], "stand-in"
+    model.StripedHyena, utils.dotdict = StandIn, dotdict
+    pkg.model, pkg.utils = model, utils
+    for name, mod in (("stripedhyena", pkg), ("stripedhyena.model", model), ("stripedhyena.utils", utils)):
+        monkeypatch.setitem(sys.modules, name, mod)
+
+
+def test_real_reference_bridge_runs_against_a_stand_in_package(monkeypatch):
+    from oracle import real_reference as RR
+    if RR.available() is not None and RR.available() != "stand-in":
+        pytest.skip("the real package is importable: the next test is the one that matters")
+    _install_stand_in_package(monkeypatch)
+    assert RR.available() == "stand-in"
+    rep = RR.compare()
+    assert rep["keys_real_minus_oracle"] == [] and rep["keys_oracle_minus_real"] == []
+    for mode in ("fp32", "bf16"):
+        r = rep[mode]
+        assert r["state_keys_equal"] and r["scale"] > 1.0
+        assert max(r["stateless"], r["prefill"], r["steps"], r["state"], r["fir_state"]) == 0.0     # same arithmetic on both sides: plumbing only
+    # the bench's CPU leg: 7B-like depth in the memory of two blocks
+    cfg = O.tiny_config(num_layers=5, attn_layer_idxs=(1, 3), hidden_size=256, num_heads=2)
+    m = RR.build(cfg, None, torch.float32, share_blocks=True)
+    assert m.blocks[0].projections.weight.data_ptr() == m.blocks[2].projections.weight.data_ptr() == m.blocks[4].projections.weight.data_ptr()
+    assert m.blocks[1].inner_mha_cls.Wqkv.weight.data_ptr() == m.blocks[3].inner_mha_cls.Wqkv.weight.data_ptr()
+    ids = torch.randint(0, 4, (1, 33)) * 3 + 65
+    assert torch.isfinite(RR._run(m, ids).float()).all()
+
+
+def test_oracle_against_the_real_stripedhyena_package():
+    """SURVEY.md A.9's verify-first checklist.  Skipped wherever `import stripedhyena` fails -- which is everywhere this repo has been
+    built or run so far; the oracle's "parity unpinned" label stands until this test has passed somewhere."""
+    from oracle import real_reference as RR
+    ver = RR.available()
+    if ver is None or ver == "stand-in":
+        pytest.skip("stripedhyena is not importable here (requirements.txt:1 of the reference pins 0.2.2; no index, no wheel): parity stays unpinned")
+    for kw in ({}, {"extra": {"use_interpolated_rotary_pos_emb": True, "rotary_emb_scaling_factor": 16}}, {"num_layers": 4, "attn_layer_idxs": (1, 3), "seed": 11}):
+        rep = RR.compare(**kw)
+        assert rep["keys_real_minus_oracle"] == [] and rep["keys_oracle_minus_real"] == [], rep
+        f, b = rep["fp32"], rep["bf16"]
+        assert f["state_keys_equal"] and b["state_keys_equal"]
+        for k in ("stateless", "prefill", "steps"):
+            assert f[k] <= 2e-4 * f["scale"], (kw, k, f)           # fp32 graph vs fp32 graph: summation order only
+            assert b[k] <= 0.05 * b["scale"], (kw, k, b)           # bf16 rounding points may differ by an ulp per op
+        assert f["state"] <= 1e-4 * max(1.0, f["scale"]) and f["fir_state"] <= 1e-5 * max(1.0, f["scale"]), (kw, f)
