@@ -1,6 +1,9 @@
 """Token sampling with the semantics of stripedhyena.sample.sample (call site
 evo/generation.py:162-167): greedy when top_k == 1, else top-k -> temperature -> top-p
--> multinomial.  512-way logits per row: host-side torch ops, not a hot path."""
+-> multinomial.  512-way logits per row: host-side torch ops, not a hot path.
+Every op runs in the logits' own dtype, like the code it mirrors (stripedhyena/sample.py is flash_attn's
+utils/generation.py:70-98): the same logits and the same torch seed give the same picks -- checked against flash_attn's function
+(tests/test_oracle.py) and, through the reference's generation loop, in tests/test_reference_host_golden.py."""
 import torch
 
 
@@ -27,8 +30,8 @@ def sample(logits: torch.Tensor, top_k: int = 1, top_p: float = 0.0, temperature
         if temperature != 1.0:
             kept = kept / temperature
         _mask_top_p(kept, top_p)
-        choice = torch.multinomial(torch.softmax(kept.float(), dim=-1), num_samples=1).squeeze(-1)
+        choice = torch.multinomial(torch.softmax(kept, dim=-1), num_samples=1).squeeze(-1)
         return kept_idx[rows, choice]
     scaled = logits / temperature if temperature != 1.0 else logits.clone()
     _mask_top_p(scaled, top_p)
-    return torch.multinomial(torch.softmax(scaled.float(), dim=-1), num_samples=1).squeeze(-1)
+    return torch.multinomial(torch.softmax(scaled, dim=-1), num_samples=1).squeeze(-1)

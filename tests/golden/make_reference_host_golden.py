@@ -6,8 +6,8 @@ reductions, the generation loop's state protocol (which slices of the prompt the
 handed at every call, quirks Q1-Q4 included) and checkpoint ingest (HF repo / revision, 'backbone.' strip, tied unembed,
 YAML config, strict load, dtype policy call order).  Those files import `stripedhyena`, which does not exist here
  -- so this script registers a stand-in `stripedhyena` package whose `StripedHyena` is a recorder, whose
-`sample` is the oracle's restatement (only its greedy branch, argmax, is exercised) and whose `dotdict` is a plain
-attribute dict, imports the reference's modules UNMODIFIED from /root/reference, and drives them on CPU with the
+`sample` is flash_attn.utils.generation.sample (installed here; the function stripedhyena/sample.py copies) and whose `dotdict`
+is a plain attribute dict, imports the reference's modules UNMODIFIED from /root/reference, and drives them on CPU with the
 oracle model (oracle/stripedhyena_oracle.py) standing where the real model would.
 
 What is NOT pinned by this: the model arithmetic (the oracle stays a restatement; "parity unpinned" in its header stands).
@@ -68,7 +68,8 @@ class dotdict(dict):
 def install_stand_in():
     pkg = types.ModuleType("stripedhyena")
     pkg.__path__ = []
-    for name, attrs in (("model", {"StripedHyena": Recorder}), ("sample", {"sample": O.sample}), ("utils", {"dotdict": dotdict}),
+    from flash_attn.utils.generation import sample as flash_attn_sample       # the code stripedhyena/sample.py copies; pure torch
+    for name, attrs in (("model", {"StripedHyena": Recorder}), ("sample", {"sample": flash_attn_sample}), ("utils", {"dotdict": dotdict}),
                         ("tokenizer", {})):
         mod = types.ModuleType("stripedhyena." + name)
         mod.__dict__.update(attrs)
@@ -171,6 +172,17 @@ def generation_cases(RG, RS, RT, arrays):
     run("prompt_forcing_q1", PROMPTS, n_tokens=5, cached_generation=True, force_prompt_threshold=3)
     run("prepend_bos", PROMPTS, n_tokens=5, cached_generation=True, prepend_bos=True)
     run("one_token", ["ACGT"], n_tokens=1, cached_generation=True)
+
+    # sampled (not greedy): one torch.multinomial draw per step from the global generator, so the seed fixes the strings
+    def run_sampled(tag, prompts, seed, **kw):
+        model = OracleAsModel(cfg, sd, torch.float64)
+        torch.manual_seed(seed)
+        texts, scores = RG.generate(prompts, model, tok, verbose=0, device="cpu", **kw)
+        out[tag] = {"prompts": prompts, "seed": seed, "kwargs": kw, "texts": texts, "scores": [float(s) for s in scores], "calls": model.calls}
+
+    run_sampled("sampled_topk4", PROMPTS, 123, n_tokens=8, cached_generation=True, top_k=4, temperature=0.8)
+    run_sampled("sampled_topk50_topp", PROMPTS, 124, n_tokens=8, cached_generation=True, top_k=50, top_p=0.7, temperature=1.0)
+    run_sampled("sampled_full_vocab", ["ACGTAC"], 125, n_tokens=6, cached_generation=True, top_k=0, top_p=0.9, temperature=1.2)
 
     # Generator.generate directly: returned tensors, then a resumed call on the returned state (evo/generation.py:105-114,140-148)
     model = OracleAsModel(cfg, sd, torch.float64)
@@ -376,7 +388,7 @@ def main():
     arrays = {}
     doc = {"generated_by": "tests/golden/make_reference_host_golden.py",
            "reference_modules": {m.__name__: hashlib.sha256(open(m.__file__, "rb").read()).hexdigest()[:16] for m in (RG, RM, RS, RT)},
-           "stand_ins": "stripedhyena.model.StripedHyena = recorder; stripedhyena.sample.sample = oracle.sample (greedy branch only); stripedhyena.utils.dotdict = attribute dict; "
+           "stand_ins": "stripedhyena.model.StripedHyena = recorder; stripedhyena.sample.sample = flash_attn.utils.generation.sample; stripedhyena.utils.dotdict = attribute dict; "
                         "the model object = oracle/stripedhyena_oracle.OracleStripedHyena (restatement, unpinned)",
            "tokenizer": tokenizer_cases(RT)}
     doc["scoring"] = scoring_cases(RS, RT, arrays)

@@ -127,6 +127,19 @@ def test_generate_matches_the_reference(ref, case):
         assert (math.isnan(g) and math.isnan(w)) or abs(g - w) <= 1e-5 * max(1.0, abs(w))     # Q3's alignment is part of the number
 
 
+@pytest.mark.parametrize("case", ["sampled_topk4", "sampled_topk50_topp", "sampled_full_vocab"])
+def test_sampled_generation_matches_the_reference_under_the_same_seed(ref, case):
+    """Not greedy: the reference's loop draws one torch.multinomial per step from the global generator (its `sample` here is
+    flash_attn.utils.generation.sample, the function stripedhyena/sample.py copies); evo_b200's host loop and host sampler must
+    consume the generator identically -- same seed, same strings, same scores."""
+    want = ref[0]["generation"][case]
+    model = OracleAsModel()
+    torch.manual_seed(want["seed"])
+    texts, scores = evo_b200.generate(want["prompts"], model, CharLevelTokenizer(512), verbose=0, device="cpu", **want["kwargs"])
+    assert texts == want["texts"] and model.calls == want["calls"]
+    assert np.allclose(scores, want["scores"], rtol=1e-5, atol=1e-5)
+
+
 def test_uncached_generation_where_the_reference_raises(ref):
     """evo/generation.py:132 reads `prefilled`, which is only assigned when generation is cached or a state is passed in: the
     reference's generate(cached_generation=False) -- its default -- dies with UnboundLocalError before the first forward.
