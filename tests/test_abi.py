@@ -60,3 +60,38 @@ def test_sass_has_tcgen05_and_tma():
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass
     assert "HMMA.16816" not in sass     # no legacy mma.sync tensor path
+
+
+def test_header_is_plain_c_and_a_c_host_binds_every_entry_point(tmp_path):
+    """include/evo_b200.h is the boundary for ANY host: it must compile as C99 and as C++ on its own, and a C program that
+    #includes it and dlopen()s the library must resolve every declared entry point and get answers from the two that need no
+    GPU (no torch, no Python anywhere near this binding)."""
+    import shutil
+    import subprocess
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("gcc / g++ not available")
+    hdr = os.path.join(ROOT, "include", "evo_b200.h")
+    for cmd in ([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                [gxx, "-std=c++11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    names = header_functions()
+    src = tmp_path / "host.c"
+    src.write_text(
+        '#include <dlfcn.h>\n#include <stdio.h>\n#include "evo_b200.h"\n'
+        "int main(int argc, char** argv) {\n"
+        "  void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);\n"
+        '  if (!h) { fprintf(stderr, "dlopen: %s\\n", dlerror()); return 2; }\n'
+        "  const char* names[] = {" + ", ".join(f'"{n}"' for n in names) + "};\n"
+        "  int missing = 0;\n"
+        "  for (unsigned i = 0; i < sizeof(names) / sizeof(names[0]); ++i) if (!dlsym(h, names[i])) { fprintf(stderr, \"missing %s\\n\", names[i]); ++missing; }\n"
+        "  int (*version)(void) = (int (*)(void))dlsym(h, \"evo_abi_version\");\n"
+        "  const char* (*last_error)(void) = (const char* (*)(void))dlsym(h, \"evo_last_error\");\n"
+        '  printf("%d %d %s\\n", missing, version(), last_error() ? "str" : "null");\n'
+        "  (void)argc; return missing != 0;\n}\n")
+    exe = tmp_path / "host"
+    r = subprocess.run([gcc, "-std=gnu99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-ldl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe), _lib.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["0", "1", "str"], (r.stdout, r.stderr)
