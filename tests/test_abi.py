@@ -95,3 +95,21 @@ def test_header_is_plain_c_and_a_c_host_binds_every_entry_point(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe), _lib.LIB_PATH], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.split() == ["0", "1", "str"], (r.stdout, r.stderr)
+
+
+def test_error_convention_without_a_gpu():
+    """No exception crosses the ABI: a rejected argument returns a negative code and leaves the reason in evo_last_error() before
+    anything is launched (so this runs on a GPU-less box); and a well-formed call on a box without a GPU FAILS, loudly, with the
+    CUDA runtime's reason -- there is no CPU path to fall back to."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this is the GPU-less half of the error convention")
+    lib = _lib.lib()
+    p = _lib.GemmParams(A=0x1000, lda=100, W=0x2000, C=0x3000, ldc=64, bias=None, residual=None, ldr=64, M=4, N=64, K=100, epilogue=0, variant=0)
+    assert lib.evo_gemm(ctypes.byref(p), None) < 0 and b"K (100) must be a multiple of 64" in lib.evo_last_error()
+    assert lib.evo_sample(None, None, 2, 2000, 1, 0.0, 1.0, 0, 0, None) < 0 and b"vocabulary 2000 unsupported" in lib.evo_last_error()
+    assert lib.evo_kv_append(None, None, 1, 10, 2, 128, 10, 16, None) < 0 and b"exceeds the KV cache (16)" in lib.evo_last_error()   # mha.py:367
+    with pytest.raises(_lib.EvoError, match="exceeds the KV cache"):
+        _lib.check(lib.evo_kv_append(None, None, 1, 10, 2, 128, 10, 16, None), "evo_kv_append")
+    rc = lib.evo_rmsnorm(ctypes.c_void_p(0x1000), ctypes.c_void_p(0x2000), ctypes.c_void_p(0x3000), 4, 4096, 1e-6, None)
+    assert rc < 0 and b"failed" in lib.evo_last_error()
