@@ -3,7 +3,7 @@ evo/generation.py:162-167): greedy when top_k == 1, else top-k -> temperature ->
 -> multinomial.  512-way logits per row: host-side torch ops, not a hot path.
 Every op runs in the logits' own dtype, like the code it mirrors (stripedhyena/sample.py is flash_attn's
 utils/generation.py:70-98): the same logits and the same torch seed give the same picks -- checked against flash_attn's function
-(tests/test_oracle.py) and, through the reference's generation loop, in tests/test_reference_host_golden.py."""
+and, through the reference's own generation loop, against fixtures made by running it (tests/golden/)."""
 import torch
 
 
